@@ -1,0 +1,162 @@
+/*
+ * score_b200.h — C ABI of the B200-native SCORE solver (libscore_b200.so).
+ *
+ * Drop-in boundary for the hot path of MarineRoboticsGroup/score:
+ *   score/solve_score.py:54-86   solve_score(data, relaxation_type)
+ * i.e. everything the reference does between "I have a FactorGraphData" and
+ * "I have relaxed + rounded variable values":
+ *   model build        score/utils/gurobi_utils.py:173-187  (initialize_model)
+ *   barrier solve      score/solve_score.py:76               (model.optimize())
+ *   value extraction   score/utils/gurobi_utils.py:114-136   (get_variable_values)
+ *
+ * The Python wrapper (score_b200/solve_score.py) does the name -> index lowering
+ * and the dict packing; everything numeric happens behind these entry points on
+ * the GPU.  There is no CPU fallback: every call fails with SCORE_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Conventions
+ *   - plain C types only; all arrays are caller-owned; pointers in ScoreProblemDesc
+ *     may be host OR device pointers (copied with cudaMemcpyDefault at create time);
+ *     output pointers of the getters are HOST pointers unless stated otherwise.
+ *   - indices are int32, zero based, instance-local; sizes are int64.
+ *   - return value 0 on success, negative ScoreStatus on error; the message is
+ *     available from score_last_error() (thread-local).
+ *   - one handle is used from one host thread at a time.
+ *
+ * Column / row order (bit-exact with the reference's variable creation order,
+ * gurobi_utils.py:233-310 and objective accumulation order :358-377):
+ *   columns: pose p -> p*d*(d+1) + r*(d+1) + c   (c<d: R[r,c], c==d: t[r])
+ *            landmark q -> P*d*(d+1) + q*d + r
+ *            QCQP delta_k[r] -> P*d*(d+1) + L*d + k*d + r ; SOCP delta_k -> ... + k
+ *   rows:    edges (odometry chains in order, then loop closures): d translation
+ *            rows then d*d rotation rows (row-major) each; then ranges; then
+ *            landmark priors.
+ */
+#ifndef SCORE_B200_H_
+#define SCORE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SCORE_OK = 0,
+  SCORE_ERR_INVALID = -1,   /* bad argument / inconsistent description          */
+  SCORE_ERR_CUDA = -2,      /* CUDA runtime failure or no usable device         */
+  SCORE_ERR_STATE = -3,     /* call out of order (e.g. get_solution before solve) */
+  SCORE_ERR_ALLOC = -4
+} ScoreStatus;
+
+enum { SCORE_RELAX_QCQP = 0, SCORE_RELAX_SOCP = 1 };
+
+/* Which matrix score_get_csr returns. */
+enum {
+  SCORE_CSR_FULL = 0,     /* the reference's least-squares matrix incl. delta columns (assembly parity) */
+  SCORE_CSR_REDUCED = 1,  /* operator the solver iterates with: pose+landmark columns only              */
+  SCORE_CSR_REDUCED_T = 2 /* its transpose (CSR of B^T)                                                 */
+};
+
+/*
+ * Lowered factor graph, structure-of-arrays.  A batch of independent instances is
+ * the concatenation of their arrays plus the *_off offset tables (n_instances+1
+ * entries each; may be NULL when n_instances == 1).
+ *
+ * Replaces the dict-of-MVar bookkeeping of VariableCollection
+ * (gurobi_utils.py:53-136) and the per-factor Python loops (:233-526).
+ */
+typedef struct {
+  int32_t dim;          /* 2 or 3 (is_dimension, gurobi_utils.py:37-50)            */
+  int32_t relaxation;   /* SCORE_RELAX_QCQP / SCORE_RELAX_SOCP (:26-28)             */
+  int32_t n_instances;
+  int32_t reserved0;
+  int64_t P, L, E, K, Lp;      /* totals over the batch                             */
+  int64_t n_seg;               /* odometry chain segments (paths of consecutive poses) */
+  const int32_t *pose_off, *lm_off, *edge_off, *rng_off, *prior_off; /* [n_instances+1] */
+  const int32_t *seg_ptr;      /* [n_seg+1] global pose index where each segment starts */
+  const int32_t *seg_inst;     /* [n_seg] owning instance                              */
+  const int32_t *link_edge;    /* [P] global edge id of the odometry edge (p-1 -> p), -1 at segment starts */
+  /* relative-pose factors (odometry then loop closures), get_relative_pose_cost_expression :504-526 */
+  const int32_t *edge_i, *edge_j;   /* [E] instance-local pose indices (base, to)   */
+  const double *edge_t;             /* [E*d]   measured translation                 */
+  const double *edge_R;             /* [E*d*d] measured rotation, row-major         */
+  const double *edge_k, *edge_tau;  /* [E] translation / rotation precision         */
+  /* range factors, get_single_range_cost :475-501 */
+  const int32_t *rng_a, *rng_b;     /* [K] translation owner: pose p -> p, landmark q -> P_inst + q */
+  const double *rng_dist, *rng_w;   /* [K] measured distance, precision             */
+  /* landmark priors, get_all_landmark_prior_costs :433-446 */
+  const int32_t *prior_l;           /* [Lp] instance-local landmark index           */
+  const double *prior_t;            /* [Lp*d]                                       */
+  const double *prior_w;            /* [Lp]                                         */
+} ScoreProblemDesc;
+
+typedef struct {
+  int32_t device;          /* CUDA device ordinal                                   */
+  int32_t max_newton;      /* outer (semismooth Newton) iteration cap, <=0: default  */
+  int32_t max_cg;          /* inner PCG iteration cap per Newton step, <=0: default  */
+  int32_t max_ticks;       /* global cap on solver ticks, <=0: default               */
+  double kkt_tol;          /* relative KKT tolerance, <=0: 1e-6    */
+  double cg_forcing;       /* inexact-Newton forcing term eta, <=0: 0.1              */
+  int32_t ticks_per_launch;/* ticks recorded per CUDA-graph replay, <=0: default     */
+  int32_t verbose;
+  void *stream;            /* cudaStream_t to run on, NULL: library-owned stream     */
+} ScoreParams;
+
+/* Per-instance result record. */
+typedef struct {
+  int32_t solved;        /* 1: rel KKT <= tol (maps to SolverResults.solved)          */
+  int32_t newton_iters;
+  int32_t cg_iters;      /* total PCG iterations = operator applications            */
+  int32_t ls_failures;
+  double objective;      /* f(x) = sum w (Bx-b)^2                                    */
+  double rel_kkt, r_stat, r_gap;
+} ScoreInstanceStats;
+
+typedef struct {
+  int32_t n_instances, n_solved;
+  int64_t ticks;           /* solver ticks executed (each = one operator application per active instance) */
+  int64_t kernel_launches; /* kernels launched by this call (incl. inside graphs)    */
+  double assemble_ms, setup_ms, solve_ms, extract_ms, total_ms; /* CUDA-event times on the solver stream */
+  int64_t nnz_reduced, rows, cols;  /* operator size over the batch                  */
+  double algorithmic_bytes;         /* sum over ticks of the bytes the active instances must move */
+} ScoreStats;
+
+typedef struct ScoreHandle_ *ScoreHandle;
+
+/* Upload a lowered problem.  (VariableCollection + data plumbing.) */
+int score_create(const ScoreProblemDesc *desc, int32_t device, ScoreHandle *out);
+
+/* Assemble, precondition, solve and round.  Replaces initialize_model + model.optimize()
+ * (solve_score.py:72-85).  inst_stats may be NULL or point to n_instances records. */
+int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats *stats, ScoreInstanceStats *inst_stats);
+
+/* Sizes of the full variable vector, for buffer allocation. */
+int score_get_sizes(ScoreHandle h, int64_t *n_cols_full, int64_t *n_rows_full, int64_t *nnz_full);
+
+/* Solution in the reference's layouts (get_variable_values, gurobi_utils.py:114-136):
+ *   pose_blocks   [P*d*(d+1)]  relaxed [R|t] row-major (Var.X of each pose MVar)
+ *   pose_rounded  [P*d*d]      nearest SO(d) rotation (round_to_special_orthogonal)
+ *   landmarks     [L*d]
+ *   dist          [K*d] (QCQP) or [K] (SOCP)
+ * any pointer may be NULL. */
+int score_get_solution(ScoreHandle h, double *pose_blocks, double *pose_rounded, double *landmarks, double *dist);
+
+/* Assembled matrix (which = SCORE_CSR_*), instance `inst` of the batch, instance-local
+ * row/column numbering.  Pass NULL arrays to query sizes only.  weights/rhs have n_rows
+ * entries (only filled for SCORE_CSR_FULL / _REDUCED). */
+int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
+                  int32_t *indptr, int32_t *indices, double *values, double *weights, double *rhs);
+
+/* Stand-alone SO(d) rounding of n d x d matrices (host pointers) on the device:
+ * round_to_special_orthogonal, score/utils/matrix_utils.py:59-79. */
+int score_round_so(int32_t dim, int64_t n, const double *mats, double *out, int32_t device);
+
+void score_destroy(ScoreHandle h);
+const char *score_last_error(void);
+const char *score_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCORE_B200_H_ */

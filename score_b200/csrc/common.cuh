@@ -1,0 +1,137 @@
+// Shared device-side structures and helpers for libscore_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/score_b200.h"
+
+namespace score {
+
+constexpr int kRowsPerBlock = 768;  // divisible by 2 and 3 so a range's d rows never straddle blocks
+constexpr int kColsPerBlock = 768;
+constexpr int kThreads = 256;
+constexpr int kSegThreads = 128;  // chain-scan CTA width
+constexpr int kNumCand = 24;      // line-search candidates 2^(1 - c/2); slot kNumCand is a = 0
+constexpr int kLsSums = kNumCand + 1 + 3;
+
+enum Phase : int { PH_CG = 0, PH_LS = 1, PH_DONE = 2 };
+enum ColKind : int { CB_POSE = 0, CB_LANDMARK = 1 };
+
+// Work descriptor of one CTA of a row-pass / column-pass kernel.  A CTA never
+// spans two instances, so per-instance partial sums are reduced in a fixed order.
+struct BlockDesc {
+  int inst, i0, i1, kind;
+};
+
+// Per-instance solver state, owned by the controller kernels.
+struct InstState {
+  int phase, skip_ls, end_cg, solved;
+  int newton_it, cg_it, total_cg, ls_fail;
+  double alpha, beta, rs, rs0, lam, eta, step;
+  double F, kkt, r_stat, r_gap, gnorm, xnorm, pt;
+};
+
+struct DevProblem {
+  int d, blk, rpe, npe;  // dim, d*(d+1), rows per edge, nnz per edge
+  int relax, n_inst;
+  int P, L, E, K, Lp, n_seg;
+  int nz, m, nnz;  // reduced operator: columns, rows, non-zeros over the batch
+  // instance offset tables [n_inst+1]
+  int *pose_off, *lm_off, *edge_off, *rng_off, *prior_off;
+  int *zoff, *roff, *nnzoff;
+  int *seg_ptr, *seg_inst, *link_edge;
+  int *seg_begin;  // [n_inst+1] first segment of each instance
+  // factors
+  int *edge_i, *edge_j;
+  double *edge_t, *edge_R, *edge_k, *edge_tau;
+  int *rng_a, *rng_b;
+  double *rng_dist, *rng_w;
+  int *prior_l;
+  double *prior_t, *prior_w;
+  // reduced operator B (CSR) and its transpose
+  int *indptr, *cols;
+  double *vals;
+  int *t_indptr, *t_rows;
+  double *t_vals;
+  double *w, *b;
+  // odometry-chain preconditioner: G = dead-reckoned frame [Rg|tg] per pose (d x (d+1)),
+  // M = G^-T D^-1 G^-1 per pose ((d+1) x (d+1)), landmark diagonal inverse
+  double *G, *M, *lm_inv;
+};
+
+struct SolverVecs {
+  // column space
+  double *z, *dz, *r, *s, *p, *t, *ytmp;
+  // row space
+  double *res, *u, *bdz;
+  // partial sums
+  double *part_row;  // [n_row_blocks] pHp
+  double *part_ls;   // [n_row_blocks * kLsSums]
+  double *part_upd;  // [n_row_blocks * 2]  F, |delta|^2
+  double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2, p.t
+  double *part_seg;  // [n_seg] r.s over chain segments
+  double *part_lm;   // [n_inst] r.s over landmarks
+};
+
+struct BlockTables {
+  BlockDesc *rb, *cb;
+  int n_rb, n_cb;
+  int *rb_begin, *cb_begin;  // [n_inst+1]
+};
+
+struct SolverCfg {
+  int max_newton, max_cg;
+  double kkt_tol, forcing;
+};
+
+__host__ __device__ inline int find_inst(const int *off, int n_inst, int idx) {
+  // largest i with off[i] <= idx  (off has n_inst+1 entries, off[n_inst] > idx)
+  int lo = 0, hi = n_inst;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= idx)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block sum (fixed tree); result valid in thread 0.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *smem /* >= NT/32 */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double out = 0.0;
+  if (wid == 0) {
+    out = (lane < NT / 32) ? smem[lane] : 0.0;
+    out = warp_sum(out);
+  }
+  return out;
+}
+
+}  // namespace score
+
+extern thread_local std::string g_score_last_error;
+
+#define SCORE_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      g_score_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                           ":" + std::to_string(__LINE__) + ")";                                 \
+      return SCORE_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)

@@ -1,0 +1,346 @@
+// Odometry-chain preconditioner.
+//
+// Along a chain segment the odometry residuals C_p = X_{p+1} - X_p T~_p  (X_p = [R_p|t_p], T~_p the
+// measured SE(d) step; score/utils/gurobi_utils.py:504-526 written in matrix form) are an invertible
+// linear change of variables.  With G_p the dead-reckoned frame (G_{p+1} = G_p T~_p) one has
+//     X_p = ( sum_{q<=p} U_q G_q^{-1} ) G_p ,   U_first = X_first, U_q = C_{q-1},
+// so the odometry Hessian is diagonal in U and its inverse is two prefix sums wrapped in per-pose
+// (d+1)x(d+1) frame changes:  P = G . cumsum . M . cumsum^T . G^T  with  M_q = G_q^{-T} D_q^{-1} G_q^{-1},
+// D = diag(2 tau, ..., 2 tau, 2 k).  Segment bases (no odometry curvature) use the inverse of the
+// range Hessian block  sum_p 2 w_p h_p h_p^T,  h_p = (tg_p, 1);  the pinned pose gets M = 0.
+#pragma once
+#include "common.cuh"
+
+namespace score {
+
+// One thread per segment: G_p = [Rg|tg], sequential composition (setup only).
+__global__ void k_dead_reckon(DevProblem P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_seg) return;
+  const int d = P.d, blk = P.blk;
+  const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1];
+  double Rg[9], tg[3], Rn[9], tn[3];
+  for (int i = 0; i < d; ++i) {
+    tg[i] = 0.0;
+    for (int j = 0; j < d; ++j) Rg[i * d + j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int p = p0; p < p1; ++p) {
+    if (p > p0) {
+      const int e = P.link_edge[p];
+      const double *Rm = P.edge_R + (size_t)e * d * d;
+      const double *tm = P.edge_t + (size_t)e * d;
+      for (int i = 0; i < d; ++i) {
+        double acc = tg[i];
+        for (int m = 0; m < d; ++m) acc += Rg[i * d + m] * tm[m];
+        tn[i] = acc;
+        for (int j = 0; j < d; ++j) {
+          double a = 0.0;
+          for (int m = 0; m < d; ++m) a += Rg[i * d + m] * Rm[m * d + j];
+          Rn[i * d + j] = a;
+        }
+      }
+      for (int i = 0; i < d; ++i) {
+        tg[i] = tn[i];
+        for (int j = 0; j < d; ++j) Rg[i * d + j] = Rn[i * d + j];
+      }
+    }
+    double *Gp = P.G + (size_t)p * blk;
+    for (int i = 0; i < d; ++i) {
+      for (int j = 0; j < d; ++j) Gp[i * (d + 1) + j] = Rg[i * d + j];
+      Gp[i * (d + 1) + d] = tg[i];
+    }
+  }
+}
+
+// Range weight incident on each pose translation (deterministic: walks the t-column of B^T in row
+// order) and the inverse Hessian diagonal of every landmark column.
+__global__ void k_diag_setup(DevProblem P, double *wsum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = P.d, blk = P.blk;
+  if (i < P.P) {
+    const int inst = find_inst(P.pose_off, P.n_inst, i);
+    const int col = P.zoff[inst] + (i - P.pose_off[inst]) * blk + d;  // t[0] column
+    const int Ei = P.edge_off[inst + 1] - P.edge_off[inst];
+    const int Ki = P.rng_off[inst + 1] - P.rng_off[inst];
+    const int rr0 = P.roff[inst] + Ei * P.rpe, rr1 = rr0 + Ki * d;
+    double acc = 0.0;
+    for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) {
+      const int row = P.t_rows[k];
+      if (row >= rr0 && row < rr1) acc += P.w[row] * P.t_vals[k] * P.t_vals[k];
+    }
+    wsum[i] = acc;
+  } else if (i < P.P + P.L * d) {
+    const int j = i - P.P;  // global landmark coordinate index
+    const int lq = j / d, r = j % d;
+    const int inst = find_inst(P.lm_off, P.n_inst, lq);
+    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+    const int col = P.zoff[inst] + Pi * blk + (lq - P.lm_off[inst]) * d + r;
+    double acc = 0.0;
+    for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) acc += P.w[P.t_rows[k]] * P.t_vals[k] * P.t_vals[k];
+    P.lm_inv[j] = (acc > 0.0) ? 1.0 / (2.0 * acc) : 1.0;
+  }
+}
+
+// In-place inverse of a small SPD matrix (n <= 4) by Gauss-Jordan.
+__device__ inline void spd_inverse(double *A, int n) {
+  double inv[16];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int c = 0; c < n; ++c) {
+    const double piv = 1.0 / A[c * n + c];
+    for (int j = 0; j < n; ++j) {
+      A[c * n + j] *= piv;
+      inv[c * n + j] *= piv;
+    }
+    for (int i = 0; i < n; ++i) {
+      if (i == c) continue;
+      const double f = A[i * n + c];
+      for (int j = 0; j < n; ++j) {
+        A[i * n + j] -= f * A[c * n + j];
+        inv[i * n + j] -= f * inv[c * n + j];
+      }
+    }
+  }
+  for (int i = 0; i < n * n; ++i) A[i] = inv[i];
+}
+
+// One thread per pose: M_p for chain-interior poses; one extra sequential loop for segment bases.
+__global__ void k_build_M(DevProblem P, const double *wsum) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.P) return;
+  const int d = P.d, d1 = d + 1, blk = P.blk;
+  double *Mp = P.M + (size_t)p * d1 * d1;
+  const int e = P.link_edge[p];
+  if (e >= 0) {
+    // A = G^{-1} = [[Rg^T, -Rg^T tg],[0,1]] ;  M = A^T D^{-1} A
+    const double *Gp = P.G + (size_t)p * blk;
+    double A[16];
+    for (int i = 0; i < d; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < d; ++j) {
+        A[i * d1 + j] = Gp[j * d1 + i];
+        acc -= Gp[j * d1 + i] * Gp[j * d1 + d];
+      }
+      A[i * d1 + d] = acc;
+    }
+    for (int j = 0; j < d; ++j) A[d * d1 + j] = 0.0;
+    A[d * d1 + d] = 1.0;
+    const double ir = 1.0 / (2.0 * P.edge_tau[e]), it = 1.0 / (2.0 * P.edge_k[e]);
+    for (int i = 0; i < d1; ++i)
+      for (int j = 0; j < d1; ++j) {
+        double acc = 0.0;
+        for (int m = 0; m < d1; ++m) acc += A[m * d1 + i] * ((m < d) ? ir : it) * A[m * d1 + j];
+        Mp[i * d1 + j] = acc;
+      }
+    return;
+  }
+  // segment base
+  const int inst = find_inst(P.pose_off, P.n_inst, p);
+  if (p == P.pose_off[inst]) {  // pinned pose: pin_pose, gurobi_utils.py:316-333
+    for (int i = 0; i < d1 * d1; ++i) Mp[i] = 0.0;
+    return;
+  }
+  // find the segment end: next pose with link_edge < 0 or instance end
+  int q = p + 1;
+  const int pend = P.pose_off[inst + 1];
+  while (q < pend && P.link_edge[q] >= 0) ++q;
+  double H[16];
+  for (int i = 0; i < d1 * d1; ++i) H[i] = 0.0;
+  for (int pp = p; pp < q; ++pp) {
+    const double ww = 2.0 * wsum[pp];
+    if (ww == 0.0) continue;
+    const double *Gp = P.G + (size_t)pp * blk;
+    double h[4];
+    for (int i = 0; i < d; ++i) h[i] = Gp[i * d1 + d];
+    h[d] = 1.0;
+    for (int i = 0; i < d1; ++i)
+      for (int j = 0; j < d1; ++j) H[i * d1 + j] += ww * h[i] * h[j];
+  }
+  double tr = 0.0;
+  for (int i = 0; i < d1; ++i) tr += H[i * d1 + i];
+  if (!(tr > 0.0)) {
+    double sc = 1.0;
+    if (q > p + 1) sc = 1.0 / (2.0 * P.edge_k[P.link_edge[p + 1]]);
+    for (int i = 0; i < d1; ++i)
+      for (int j = 0; j < d1; ++j) Mp[i * d1 + j] = (i == j) ? sc : 0.0;
+    return;
+  }
+  for (int i = 0; i < d1; ++i) H[i * d1 + i] += 1e-9 * tr;
+  spd_inverse(H, d1);
+  for (int i = 0; i < d1 * d1; ++i) Mp[i] = H[i];
+}
+
+// z0: every segment dead-reckoned from an identity base; landmarks at the origin.
+__global__ void k_init_z(DevProblem P, double *z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nz) return;
+  const int inst = find_inst(P.zoff, P.n_inst, i);
+  const int loc = i - P.zoff[inst];
+  const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+  if (loc < Pi * P.blk)
+    z[i] = P.G[(size_t)P.pose_off[inst] * P.blk + loc];
+  else
+    z[i] = 0.0;
+}
+
+// Inclusive scan of NV doubles per thread across the CTA (plus running carry across tiles).
+template <int NV>
+__device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], double *carry) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NW = kSegThreads / 32;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, v[c], o);
+      if (lane >= o) v[c] += n;
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int c = 0; c < NV; ++c) wtot[wid][c] = v[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    double add = carry[c];
+    for (int w = 0; w < wid; ++w) add += wtot[w][c];
+    v[c] += add;
+  }
+  double ncarry = 0.0;
+  if (threadIdx.x < NV) {
+    ncarry = carry[threadIdx.x];
+    for (int w = 0; w < NW; ++w) ncarry += wtot[w][threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) carry[threadIdx.x] = ncarry;
+}
+
+// s = P r  (and the partial sums of r.s).  CTA per chain segment; CTAs past n_seg handle the
+// landmark block of one instance each.
+template <int D>
+__global__ void __launch_bounds__(kSegThreads) k_precond(DevProblem P, SolverVecs V, const InstState *st) {
+  constexpr int D1 = D + 1, NV = D * D1;
+  __shared__ double wtot[kSegThreads / 32][NV];
+  __shared__ double carry[NV];
+  __shared__ double red[kSegThreads / 32];
+  const int tid = threadIdx.x;
+  int s = blockIdx.x;
+  if (s >= P.n_seg) {
+    const int inst = s - P.n_seg;
+    if (st[inst].phase == PH_DONE) return;
+    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+    const int n = (P.lm_off[inst + 1] - P.lm_off[inst]) * D;
+    const int c0 = P.zoff[inst] + Pi * P.blk, j0 = P.lm_off[inst] * D;
+    double acc = 0.0;
+    for (int j = tid; j < n; j += kSegThreads) {
+      const double rv = V.r[c0 + j];
+      const double sv = rv * P.lm_inv[j0 + j];
+      V.s[c0 + j] = sv;
+      acc += rv * sv;
+    }
+    const double tot = block_sum<kSegThreads>(acc, red);
+    if (tid == 0) V.part_lm[inst] = tot;
+    return;
+  }
+  const int inst = P.seg_inst[s];
+  if (st[inst].phase == PH_DONE) return;
+  const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
+  const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
+
+  // ---- reverse pass: S_p = sum_{q>=p} r_q G_q^T ;  Y_p = S_p M_p
+  if (tid < NV) carry[tid] = 0.0;
+  __syncthreads();
+  for (int t0 = 0; t0 < len; t0 += kSegThreads) {
+    const int idx = t0 + tid;
+    const bool valid = idx < len;
+    const int pg = p1 - 1 - idx;
+    double v[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) v[c] = 0.0;
+    if (valid) {
+      const double *rp = V.r + colbase + (long)pg * NV;
+      const double *Gp = P.G + (size_t)pg * NV;
+      double g[NV];
+#pragma unroll
+      for (int c = 0; c < NV; ++c) g[c] = Gp[c];
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        double rb[D1];
+#pragma unroll
+        for (int c = 0; c < D1; ++c) rb[c] = rp[r * D1 + c];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double acc = rb[D] * g[c * D1 + D];
+#pragma unroll
+          for (int m = 0; m < D; ++m) acc += rb[m] * g[c * D1 + m];
+          v[r * D1 + c] = acc;
+        }
+        v[r * D1 + D] = rb[D];
+      }
+    }
+    cta_scan<NV>(v, wtot, carry);
+    if (valid) {
+      const double *Mp = P.M + (size_t)pg * D1 * D1;
+      double mm[D1 * D1];
+#pragma unroll
+      for (int c = 0; c < D1 * D1; ++c) mm[c] = Mp[c];
+      double *yp = V.ytmp + colbase + (long)pg * NV;
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D1; ++c) {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < D1; ++m) acc += v[r * D1 + m] * mm[m * D1 + c];
+          yp[r * D1 + c] = acc;
+        }
+    }
+  }
+  __syncthreads();
+  // ---- forward pass: Xh_p = sum_{q<=p} Y_q ;  s_p = Xh_p G_p
+  if (tid < NV) carry[tid] = 0.0;
+  __syncthreads();
+  double dot = 0.0;
+  for (int t0 = 0; t0 < len; t0 += kSegThreads) {
+    const int idx = t0 + tid;
+    const bool valid = idx < len;
+    const int pg = p0 + idx;
+    double v[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) v[c] = 0.0;
+    if (valid) {
+      const double *yp = V.ytmp + colbase + (long)pg * NV;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) v[c] = yp[c];
+    }
+    cta_scan<NV>(v, wtot, carry);
+    if (valid) {
+      const double *Gp = P.G + (size_t)pg * NV;
+      const double *rp = V.r + colbase + (long)pg * NV;
+      double *sp = V.s + colbase + (long)pg * NV;
+      double g[NV];
+#pragma unroll
+      for (int c = 0; c < NV; ++c) g[c] = Gp[c];
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        double tacc = v[r * D1 + D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < D; ++m) acc += v[r * D1 + m] * g[m * D1 + c];
+          sp[r * D1 + c] = acc;
+          dot += acc * rp[r * D1 + c];
+          tacc += v[r * D1 + c] * g[c * D1 + D];
+        }
+        sp[r * D1 + D] = tacc;
+        dot += tacc * rp[r * D1 + D];
+      }
+    }
+  }
+  const double tot = block_sum<kSegThreads>(dot, red);
+  if (tid == 0) V.part_seg[s] = tot;
+}
+
+}  // namespace score
