@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the solve_score hot path.
+
+Workload (BASELINE.json configs[3], the configuration "batched solves/sec" is quoted on):
+the Monte-Carlo sweep of synthetic 20-robot x 100-pose 2D range-aided SLAM instances
+(score_b200/generators.py, seeds 20221003 + i), 1024 instances per GPU, QCQP relaxation,
+every instance solved to 1e-6 relative KKT.  One "step" = one full pass of the hot path over
+the batch: on-device assembly + preconditioner setup + semismooth Newton-PCG solve + SO(d)
+rounding.  With N GPUs every rank solves its own 1024 instances (no data-path collective; weak
+scaling); `value` is instances solved per second over all ranks.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU interior-point port on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "batched solves/sec (each SOCP/QCQP instance solved to 1e-6 relative KKT)"
+UNIT = "solves/s"
+KKT_TOL = 1e-6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="score_b200", choices=["score_b200", "reference"])
+    ap.add_argument("--instances", type=int, default=1024, help="instances per GPU")
+    ap.add_argument("--robots", type=int, default=20)
+    ap.add_argument("--poses", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU-baseline step (0: one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def _gen_one(args):
+    seed, robots, poses = args
+    from score_b200 import generators
+    from score_b200.lowering import lower_manhattan_arrays
+
+    arr = generators.manhattan_2d_arrays(seed, n_robots=robots, n_steps=poses)
+    return lower_manhattan_arrays(arr, "QCQP", with_names=False)
+
+
+def make_batch(first, count, robots, poses):
+    """Lowered batch of `count` sweep instances starting at instance index `first`."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    from score_b200 import generators
+    from score_b200.lowering import concat
+
+    jobs = [(generators.MC_BASE_SEED + first + i, robots, poses) for i in range(count)]
+    workers = max(1, min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if workers > 1 and count >= 8:
+        import multiprocessing as mp
+
+        with ProcessPoolExecutor(workers, mp_context=mp.get_context("fork")) as ex:
+            probs = list(ex.map(_gen_one, jobs, chunksize=8))
+    else:
+        probs = [_gen_one(j) for j in jobs]
+    return concat(probs)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (interior-point restatement of the reference's Gurobi barrier solve)
+# ------------------------------------------------------------------------------------------------
+def _cpu_solve_one(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    seed, robots, poses = args
+    from oracle import score_oracle as so  # bench.py's CPU legs are allowed to execute the oracle
+    from score_b200 import generators
+
+    fg = generators.manhattan_2d(seed, n_robots=robots, n_steps=poses)
+    t0 = time.perf_counter()
+    prob = so.assemble(fg, so.QCQP)
+    sol = so.solve_qcqp_barrier(prob, mu_final=1e-9)
+    x = so.polish_distances(prob, sol.x)
+    kkt = so.kkt_qcqp(prob, x)["rel_kkt"]
+    return time.perf_counter() - t0, kkt, sol.objective
+
+
+def cpu_step(pool, seeds, robots, poses):
+    t0 = time.perf_counter()
+    res = list(pool.map(_cpu_solve_one, [(s, robots, poses) for s in seeds]))
+    dt = time.perf_counter() - t0
+    return dt, res
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the CPU interior-point port on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    from score_b200 import generators
+
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or cores
+    times = []
+    with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
+        # warm-up: spin the pool up on a reduced sample (tiny instances), untimed
+        for _ in range(max(1, args.warmup)):
+            cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(cores)], 4, 25)
+        kkts = []
+        for k in range(args.steps):
+            seeds = [generators.MC_BASE_SEED + k * sample + i for i in range(sample)]
+            dt, res = cpu_step(pool, seeds, args.robots, args.poses)
+            times.append(dt)
+            kkts += [r[1] for r in res]
+    total = sample * args.steps
+    value = total / sum(times)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, sample_note=f"{sample} instances per step"),
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{sample} sweep instances per step ({args.robots} robots x {args.poses} poses), one per process, "
+            f"log-barrier Newton + SuperLU (oracle/score_oracle.py) to rel KKT <= 1e-6 (max seen {max(kkts):.1e}); "
+            f"cpu: {cpu_model()}",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_note=None):
+    cfg = {
+        "workload": f"monte_carlo_sweep (BASELINE configs[3]): {args.instances} instances/GPU x "
+        f"({args.robots} robots x {args.poses} poses, 6 landmarks, ~{int(31 * args.poses * args.robots / 20)} ranges), "
+        "2D, QCQP relaxation, seeds 20221003+i, solved to 1e-6 rel KKT",
+        "instances_per_gpu": args.instances,
+        "robots": args.robots,
+        "poses_per_robot": args.poses,
+        "relaxation": "QCQP",
+        "kkt_tol": KKT_TOL,
+        "l2": "working set per GPU (~3.5 GB at 1024 instances) is far larger than the 126 MB L2; no explicit flush",
+        "parallelism": "independent instances sharded across GPUs, no data-path collective",
+    }
+    if sample_note:
+        cfg["reference_sample"] = sample_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {
+            "sm_mhz": float(np.median(sm)),
+            "sm_max_mhz": float(max(smax)),
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank, local_rank, world):
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork safety)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+
+        from score_b200 import generators
+
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or cores
+        with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
+            cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(cores)], 4, 25)  # pool spin-up
+            dt, res = cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(sample)], args.robots, args.poses)
+        cpu_baseline = {
+            "value": sample / dt,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{sample} sweep instances (seeds 20221003..+{sample - 1}), one per process over {cores} cores, "
+            f"log-barrier Newton + SuperLU (oracle/score_oracle.py) to rel KKT <= 1e-6 "
+            f"(max seen {max(r[1] for r in res):.1e}); wall {dt:.1f} s; mean per-instance {np.mean([r[0] for r in res]):.1f} s; "
+            f"cpu: {cpu_model()}",
+        }
+
+    import torch
+    import torch.distributed as dist
+
+    from score_b200 import build
+
+    build.build()
+    from score_b200.solver import KERNEL_NAMES, ScoreSolver
+
+    # generate the shard before CUDA is initialised (the generator forks worker processes)
+    prob = make_batch(rank * args.instances, args.instances, args.robots, args.poses)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    solver = ScoreSolver(prob, device=local_rank)
+
+    for _ in range(args.warmup):
+        solver.solve(kkt_tol=KKT_TOL, stream=stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    bytes_total = 0.0
+    solve_ms = 0.0
+    ticks = 0
+    n_solved = 0
+    ev0.record()
+    for _ in range(args.steps):
+        st = solver.solve(kkt_tol=KKT_TOL, stream=stream)
+        launches += st.kernel_launches
+        bytes_total += st.algorithmic_bytes
+        solve_ms += st.solve_ms
+        ticks += st.ticks
+        n_solved += st.n_solved
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        agg = torch.tensor([float(n_solved), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        n_solved_all, launches_all = int(agg[0].item()), int(agg[1].item())
+    else:
+        n_solved_all, launches_all = n_solved, launches
+    t_ms = float(t_ms.item())
+    total_instances = args.instances * world * args.steps
+    value = total_instances / (t_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: one extra step with CUDA events between the kernels of
+    # 32 early ticks (all instances still active), on the same stream
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        peak = float(json.load(f)["hbm_gbs"])
+    stp = solver.solve(kkt_tol=KKT_TOL, stream=stream, profile_ticks=32, profile_skip=8)
+    kms = stp.kernel_ms / max(1, stp.profiled_ticks)
+    dom = int(np.argmax(kms))
+    achieved = stp.kernel_bytes[dom] / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(KERNEL_NAMES[dom])
+        except (OSError, ValueError):
+            traffic = None
+    roofline = {
+        "bound": "hbm",
+        "kernel": KERNEL_NAMES[dom],
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": traffic,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)",
+        "how": "CUDA events around every kernel of 32 un-graphed ticks (ticks 8..39, every instance active) in one extra "
+        "step on the solver stream; achieved = algorithmic bytes of one launch / mean launch time",
+        "ms_per_launch": float(kms[dom]),
+        "bytes_per_launch": float(stp.kernel_bytes[dom]),
+        "tick_kernel_ms": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
+        "tick_kernel_gbs": {
+            n: (float(b / (v * 1e-3) / 1e9) if v > 0 and b > 0 else None)
+            for n, v, b in zip(KERNEL_NAMES, kms, stp.kernel_bytes)
+        },
+        "whole_solve_gbs": bytes_total / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
+    }
+
+    # ---- e2e: the same step through the public API with HOST buffers every step:
+    # score_create (H2D of the lowered arrays from pinned memory) + score_solve + score_get_solution (D2H) + destroy
+    e2e = None
+    if not args.no_e2e:
+        import dataclasses
+
+        pinned = {}
+        for f in dataclasses.fields(prob):
+            v = getattr(prob, f.name)
+            if isinstance(v, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+                pinned[f.name] = t
+        prob_pinned = dataclasses.replace(prob, **{k: t.numpy() for k, t in pinned.items()})
+        n_e2e = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(n_e2e):
+            s2 = ScoreSolver(prob_pinned, device=local_rank)
+            s2.solve(kkt_tol=KKT_TOL, stream=stream)
+            s2.solution()
+            h2d, d2h = s2.h2d_bytes, s2.d2h_bytes
+            s2.close()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": args.instances * world * n_e2e / float(dt.item()),
+            "unit": UNIT,
+            "h2d_bytes_per_step": int(h2d) * world,
+            "d2h_bytes_per_step": int(d2h) * world,
+            "steps": n_e2e,
+            "how": "per step: score_create from pinned host arrays (H2D) + score_solve + score_get_solution (D2H of relaxed "
+            "poses, rounded rotations, landmarks, distance variables) + score_destroy; host wall clock, max over ranks",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches_all,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "solved": n_solved_all,
+            "instances": total_instances,
+            "ticks_per_step": ticks / args.steps,
+            "impl": "score_b200",
+        }
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,8 @@ typedef struct {
   int32_t ticks_per_launch;/* ticks recorded per CUDA-graph replay, <=0: default     */
   int32_t verbose;
   void *stream;            /* cudaStream_t to run on, NULL: library-owned stream     */
+  int32_t profile_ticks;   /* >0: time every kernel of this many early ticks with CUDA events (un-graphed) */
+  int32_t profile_skip;    /* ticks to run before the profiled ones                  */
 } ScoreParams;
 
 /* Per-instance result record. */
@@ -120,6 +122,12 @@ typedef struct {
   double assemble_ms, setup_ms, solve_ms, extract_ms, total_ms; /* CUDA-event times on the solver stream */
   int64_t nnz_reduced, rows, cols;  /* operator size over the batch                  */
   double algorithmic_bytes;         /* sum over ticks of the bytes the active instances must move */
+  /* profile mode: summed CUDA-event time of each tick kernel over the profiled ticks, in launch order
+   * rowpass, linesearch, ctrl_a, rowupdate, colpass, precond, ctrl_b, pupdate */
+  double kernel_ms[8];
+  int64_t profiled_ticks;
+  /* algorithmic bytes of ONE launch of each tick kernel with every instance in the PCG phase */
+  double kernel_bytes[8];
 } ScoreStats;
 
 typedef struct ScoreHandle_ *ScoreHandle;

@@ -302,9 +302,26 @@ def solve_qcqp_barrier(
         r = A @ xv + r0
         return float(r @ r)
 
-    # pattern of the barrier Hessian blocks (d x d per range), assembled as COO once
-    bi = np.repeat(dcols, d, axis=1).ravel()  # row index
-    bj = np.tile(dcols, (1, d)).ravel()  # col index
+    # Schur complement on the (pose, landmark) block: the delta block of the Newton matrix is
+    # block diagonal (one d x d block per range), so it is eliminated exactly and only the
+    # smaller SPD matrix S = Hzz - Hzd Dk^-1 Hdz is factorised.
+    is_d = np.zeros(nf, bool)
+    is_d[dcols.ravel()] = True
+    zi = np.nonzero(~is_d)[0]
+    di = dcols.ravel()  # delta unknowns in range order
+    H0r = H0.tocsr()
+    Hzz = H0r[zi][:, zi].tocsc()
+    Hzd = H0r[zi][:, di].tocsr()
+    Hdz = Hzd.T.tocsr()
+    Hdd0 = np.zeros((K, d, d))
+    Hdd_full = H0r[di][:, di].tocoo()
+    blk_of = Hdd_full.row // d
+    assert np.array_equal(blk_of, Hdd_full.col // d), "delta block of the Hessian must be block diagonal"
+    np.add.at(Hdd0, (blk_of, Hdd_full.row % d, Hdd_full.col % d), Hdd_full.data)
+    kd = K * d
+    bd_indptr = np.arange(0, kd * d + 1, d)
+    bd_indices = (np.repeat(np.arange(K) * d, d * d).reshape(K, d, d) + np.arange(d)[None, None, :]).ravel()
+    eye = np.eye(d)[None]
 
     steps = 0
     mu = 1.0
@@ -315,14 +332,21 @@ def solve_qcqp_barrier(
             grad = H0 @ x + g0
             gb = (2.0 * mu / s)[:, None] * dl
             np.add.at(grad, dcols.ravel(), gb.ravel())
-            # blocks: mu * (2/s I + 4 dl dl^T / s^2)
-            blocks = (2.0 * mu / s)[:, None, None] * np.eye(d)[None] + (4.0 * mu / (s * s))[
-                :, None, None
-            ] * (dl[:, :, None] * dl[:, None, :])
-            Hb = sp.csc_matrix((blocks.ravel(), (bi, bj)), shape=(nf, nf))
-            H = (H0 + Hb).tocsc()
-            lu = spla.splu(H, permc_spec="MMD_AT_PLUS_A")
-            dx = lu.solve(-grad)
+            # barrier blocks: mu * (2/s I + 4 dl dl^T / s^2)
+            blocks = Hdd0 + (2.0 * mu / s)[:, None, None] * eye + (4.0 * mu / (s * s))[:, None, None] * (
+                dl[:, :, None] * dl[:, None, :]
+            )
+            # ranges with dist == 0 have an all-zero column: only the barrier term keeps them SPD
+            Dinv = sp.csr_matrix((np.linalg.inv(blocks).ravel(), bd_indices, bd_indptr), shape=(kd, kd))
+            S = (Hzz - (Hzd @ Dinv @ Hdz)).tocsc()
+            gz, gd_ = grad[zi], grad[di]
+            # S is SPD: symmetric ordering + no pivoting (~9x faster than the unsymmetric default)
+            lu = spla.splu(S, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+            dzv = lu.solve(-(gz - Hzd @ (Dinv @ gd_)))
+            ddv = -(Dinv @ (gd_ + Hdz @ dzv))
+            dx = np.zeros(nf)
+            dx[zi] = dzv
+            dx[di] = ddv
             steps += 1
             dec = float(-grad @ dx)
             # backtracking keeping strict feasibility

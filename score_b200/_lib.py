@@ -66,6 +66,8 @@ class ScoreParams(C.Structure):
         ("ticks_per_launch", C.c_int32),
         ("verbose", C.c_int32),
         ("stream", C.c_void_p),
+        ("profile_ticks", C.c_int32),
+        ("profile_skip", C.c_int32),
     ]
 
 
@@ -97,6 +99,9 @@ class ScoreStats(C.Structure):
         ("rows", C.c_int64),
         ("cols", C.c_int64),
         ("algorithmic_bytes", C.c_double),
+        ("kernel_ms", C.c_double * 8),
+        ("profiled_ticks", C.c_int64),
+        ("kernel_bytes", C.c_double * 8),
     ]
 
 

@@ -348,19 +348,34 @@ extern "C" int score_create(const ScoreProblemDesc *desc, int32_t device, ScoreH
   return SCORE_OK;
 }
 
-template <int D>
-static void launch_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st) {
-  const DevProblem &P = h->P;
-  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st);
-  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  k_precond<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
-  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone);
-  k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
-}
 constexpr int kKernelsPerTick = 8;
+
+// One solver tick.  `ev` (optional, kKernelsPerTick + 1 events) brackets every kernel for profiling.
+template <int D>
+static void launch_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+  const DevProblem &P = h->P;
+  int k = 0;
+  auto mark = [&]() {
+    if (ev) cudaEventRecord(ev[k++], st);
+  };
+  mark();
+  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  mark();
+  k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  mark();
+  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st);
+  mark();
+  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  mark();
+  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  mark();
+  k_precond<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
+  mark();
+  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone);
+  mark();
+  k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
+  mark();
+}
 
 extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats *stats, ScoreInstanceStats *inst_stats) {
   if (!h) {
@@ -450,6 +465,37 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     h->graph_cfg = cfg;
   }
   long ticks = 0;
+  double kernel_ms[kKernelsPerTick] = {0};
+  long profiled = 0;
+  if (prm.profile_ticks > 0) {
+    // un-graphed ticks with an event between every pair of kernels
+    const int nskip = prm.profile_skip > 0 ? prm.profile_skip : 0, nprof = prm.profile_ticks;
+    for (int t = 0; t < nskip; ++t) {
+      if (d == 2)
+        launch_tick<2>(h, cfg, st);
+      else
+        launch_tick<3>(h, cfg, st);
+    }
+    std::vector<cudaEvent_t> pev((size_t)nprof * (kKernelsPerTick + 1));
+    for (auto &e : pev) SCORE_CUDA_CHECK(cudaEventCreate(&e));
+    for (int t = 0; t < nprof; ++t) {
+      if (d == 2)
+        launch_tick<2>(h, cfg, st, &pev[(size_t)t * (kKernelsPerTick + 1)]);
+      else
+        launch_tick<3>(h, cfg, st, &pev[(size_t)t * (kKernelsPerTick + 1)]);
+    }
+    SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int t = 0; t < nprof; ++t)
+      for (int k = 0; k < kKernelsPerTick; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pev[(size_t)t * (kKernelsPerTick + 1) + k], pev[(size_t)t * (kKernelsPerTick + 1) + k + 1]);
+        kernel_ms[k] += ms;
+      }
+    for (auto &e : pev) cudaEventDestroy(e);
+    ticks += nskip + nprof;
+    launches += (long)(nskip + nprof) * kKernelsPerTick;
+    profiled = nprof;
+  }
   while (ticks < max_ticks) {
     SCORE_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, st));
     ticks += tpl;
@@ -509,6 +555,20 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     stats->rows = P.m;
     stats->cols = P.nz;
     stats->algorithmic_bytes = bytes;
+    stats->profiled_ticks = profiled;
+    for (int k = 0; k < kKernelsPerTick; ++k) stats->kernel_ms[k] = kernel_ms[k];
+    // per-launch algorithmic bytes with every instance in the PCG phase
+    const double nnz = P.nnz, m = P.m, nz = P.nz, K = P.K, Pn = P.P, blk = P.blk, d1 = d + 1;
+    const double nrb = h->T.n_rb, ncb = h->T.n_cb;
+    stats->kernel_bytes[0] = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 16.0 * m + 8.0 * (d * K + K);
+    stats->kernel_bytes[1] = 0.0;
+    stats->kernel_bytes[2] = 8.0 * nrb;
+    stats->kernel_bytes[3] = 0.0;
+    stats->kernel_bytes[4] = 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
+    stats->kernel_bytes[5] = 32.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);
+    stats->kernel_bytes[6] = 8.0 * (P.n_seg + P.n_inst);
+    stats->kernel_bytes[7] = 48.0 * nz;
+    (void)ncb;
   }
   for (auto &e : ev) cudaEventDestroy(e);
   return SCORE_OK;

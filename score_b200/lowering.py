@@ -253,7 +253,7 @@ def lower_factor_graph(fg, relaxation: str = QCQP_RELAXATION) -> LoweredProblem:
     )
 
 
-def lower_manhattan_arrays(arr: dict, relaxation: str = QCQP_RELAXATION) -> LoweredProblem:
+def lower_manhattan_arrays(arr: dict, relaxation: str = QCQP_RELAXATION, with_names: bool = True) -> LoweredProblem:
     """Lower the array form produced by ``generators.manhattan_2d_arrays`` without
     materialising Python factor objects (identical result to lowering
     ``arrays_to_factor_graph(arr)``; used for the 1024-instance sweep)."""
@@ -272,9 +272,13 @@ def lower_manhattan_arrays(arr: dict, relaxation: str = QCQP_RELAXATION) -> Lowe
     i32 = lambda *v: np.asarray(v, np.int32)
     from .generators import _chain_prefix
 
-    pose_names = [f"{_chain_prefix(r)}{t}" for r in range(R) for t in range(S)]
-    lm_names = [f"L{q}" for q in range(L)]
-    all_names = pose_names + lm_names
+    if with_names:
+        pose_names = [f"{_chain_prefix(r)}{t}" for r in range(R) for t in range(S)]
+        lm_names = [f"L{q}" for q in range(L)]
+        all_names = pose_names + lm_names
+        range_keys = [(all_names[a], all_names[b]) for a, b in zip(arr["rng_a"], arr["rng_b"])]
+    else:  # throughput runs: results are consumed as arrays, no dict packing
+        pose_names, lm_names, range_keys = [], [], []
     return LoweredProblem(
         dim=d,
         relaxation=relaxation,
@@ -302,7 +306,7 @@ def lower_manhattan_arrays(arr: dict, relaxation: str = QCQP_RELAXATION) -> Lowe
         prior_w=np.zeros(0),
         pose_names=[pose_names],
         landmark_names=[lm_names],
-        range_keys=[[(all_names[a], all_names[b]) for a, b in zip(arr["rng_a"], arr["rng_b"])]],
+        range_keys=[range_keys],
     )
 
 

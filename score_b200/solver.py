@@ -27,6 +27,12 @@ class SolveStats:
     cols: int
     algorithmic_bytes: float
     instances: np.ndarray  # structured array, one record per instance
+    kernel_ms: Optional[np.ndarray] = None  # profile mode: per-kernel event time summed over profiled ticks
+    profiled_ticks: int = 0
+    kernel_bytes: Optional[np.ndarray] = None  # algorithmic bytes of one launch of each tick kernel
+
+
+KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_colpass", "k_precond", "k_ctrl_b", "k_pupdate"]
 
 
 _INST_DTYPE = np.dtype(
@@ -115,6 +121,8 @@ class ScoreSolver:
         cg_forcing: float = 0.0,
         ticks_per_launch: int = 0,
         stream: int = 0,
+        profile_ticks: int = 0,
+        profile_skip: int = 0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
@@ -122,6 +130,7 @@ class ScoreSolver:
         prm.kkt_tol, prm.cg_forcing = kkt_tol, cg_forcing
         prm.ticks_per_launch = ticks_per_launch
         prm.stream = C.c_void_p(stream) if stream else None
+        prm.profile_ticks, prm.profile_skip = profile_ticks, profile_skip
         st = _lib.ScoreStats()
         inst = np.zeros(self.prob.n_instances, dtype=_INST_DTYPE)
         _check(self._lib.score_solve(self._h, C.byref(prm), C.byref(st),
@@ -129,6 +138,8 @@ class ScoreSolver:
         self.last_stats = SolveStats(
             st.n_instances, st.n_solved, st.ticks, st.kernel_launches, st.assemble_ms, st.setup_ms, st.solve_ms,
             st.extract_ms, st.total_ms, st.nnz_reduced, st.rows, st.cols, st.algorithmic_bytes, inst,
+            kernel_ms=np.array(st.kernel_ms[:]), profiled_ticks=int(st.profiled_ticks),
+            kernel_bytes=np.array(st.kernel_bytes[:]),
         )
         return self.last_stats
 
