@@ -103,6 +103,11 @@ typedef struct {
   void *stream;            /* cudaStream_t to run on, NULL: library-owned stream     */
   int32_t profile_ticks;   /* >0: time every kernel of this many early ticks with CUDA events (un-graphed) */
   int32_t profile_skip;    /* ticks to run before the profiled ones                  */
+  /* interior-point path following (0: defaults) */
+  double mu0;              /* initial barrier parameter, default 1.0; < 0: no barrier (plain semismooth Newton) */
+  double mu_factor;        /* barrier reduction per centred stage, default 0.1       */
+  double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 4 */
+  double mu_min;           /* smallest barrier parameter, default 1e-16              */
 } ScoreParams;
 
 /* Per-instance result record. */
@@ -110,7 +115,7 @@ typedef struct {
   int32_t solved;        /* 1: rel KKT <= tol (maps to SolverResults.solved)          */
   int32_t newton_iters;
   int32_t cg_iters;      /* total PCG iterations = operator applications            */
-  int32_t ls_failures;
+  int32_t ls_failures;   /* Newton steps whose line search found no decreasing candidate */
   double objective;      /* f(x) = sum w (Bx-b)^2                                    */
   double rel_kkt, r_stat, r_gap;
 } ScoreInstanceStats;
@@ -123,11 +128,12 @@ typedef struct {
   int64_t nnz_reduced, rows, cols;  /* operator size over the batch                  */
   double algorithmic_bytes;         /* sum over ticks of the bytes the active instances must move */
   /* profile mode: summed CUDA-event time of each tick kernel over the profiled ticks, in launch order
-   * rowpass, linesearch, ctrl_a, rowupdate, colpass, precond, ctrl_b, pupdate */
-  double kernel_ms[8];
+   * rowpass, linesearch, ctrl_a, rowupdate, coarse_build, colpass, precond_rev, coarse_apply, precond_fwd,
+   * ctrl_b, pupdate */
+  double kernel_ms[12];
   int64_t profiled_ticks;
   /* algorithmic bytes of ONE launch of each tick kernel with every instance in the PCG phase */
-  double kernel_bytes[8];
+  double kernel_bytes[12];
 } ScoreStats;
 
 typedef struct ScoreHandle_ *ScoreHandle;

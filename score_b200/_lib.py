@@ -68,6 +68,10 @@ class ScoreParams(C.Structure):
         ("stream", C.c_void_p),
         ("profile_ticks", C.c_int32),
         ("profile_skip", C.c_int32),
+        ("mu0", C.c_double),
+        ("mu_factor", C.c_double),
+        ("center_tol", C.c_double),
+        ("mu_min", C.c_double),
     ]
 
 
@@ -99,9 +103,9 @@ class ScoreStats(C.Structure):
         ("rows", C.c_int64),
         ("cols", C.c_int64),
         ("algorithmic_bytes", C.c_double),
-        ("kernel_ms", C.c_double * 8),
+        ("kernel_ms", C.c_double * 12),
         ("profiled_ticks", C.c_int64),
-        ("kernel_bytes", C.c_double * 8),
+        ("kernel_bytes", C.c_double * 12),
     ]
 
 

@@ -33,6 +33,8 @@ struct ScoreHandle_ {
   // host copies of the offset tables
   std::vector<int> pose_off, lm_off, edge_off, rng_off, prior_off, zoff, roff, nnzoff, seg_begin;
   std::vector<int> rb_begin, cb_begin;
+  std::vector<int> c_off, c_moff, c_n, c_nb;
+  int c_nmax = 0;
   std::vector<void *> allocs;
   cudaStream_t own_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -91,24 +93,27 @@ int fetch_offsets(const int32_t *src, int n_inst, int64_t total, std::vector<int
 int grid_for(long n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // Bytes one PCG tick of an instance must move (fp64 values, int32 indices; DESIGN.md "algorithmic bytes").
-double bytes_cg_tick(int d, double nnz, double m, double nz, double K, double Pn) {
+double bytes_cg_tick(int d, double nnz, double m, double nz, double K, double Pn, double nc) {
   const double blk = d * (d + 1), d1 = d + 1;
   double b = 0.0;
-  b += 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * 2.0 * m + 8.0 * (d * K + K);  // rowpass
-  b += 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * 5.0 * nz;                      // colpass
-  b += 8.0 * 4.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);                            // precond (r, ytmp w+r, s; G twice, M)
-  b += 8.0 * 6.0 * nz;                                                               // pupdate
+  b += 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * 2.0 * m + 8.0 * (d * K + 2.0 * K);  // rowpass
+  b += 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * 5.0 * nz;                            // colpass
+  b += 8.0 * 5.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);   // precond rev+fwd (r twice, ytmp w+r, s; G twice, M)
+  b += 8.0 * (nc * nc + 3.0 * nc);                           // coarse apply
+  b += 8.0 * 3.0 * nz;                                       // pupdate
   return b;
 }
-double bytes_ls_tick(int d, double nnz, double m, double nz, double K, double Pn) {
+double bytes_ls_tick(int d, double nnz, double m, double nz, double K, double Pn, double nc) {
   const double blk = d * (d + 1), d1 = d + 1;
   double b = 0.0;
   b += 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * m;                  // rowpass: bdz = B dz
   b += 8.0 * 2.0 * m + 8.0 * (m - d * K) + 16.0 * K;                     // linesearch: res, bdz, w(plain), r~, w(range)
-  b += 8.0 * 5.0 * m + 8.0 * K;                                          // rowupdate: res rw, bdz, w, u
+  b += 8.0 * 5.0 * m + 8.0 * 3.0 * K;                                    // rowupdate: res rw, bdz, w, u; r~, ctan, crad
+  b += 8.0 * (d * K + 6.0 * K) + 8.0 * nc * nc;                          // coarse build: res, factors, slots, G column; inverse out
   b += 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * 5.0 * nz;           // colpass: z rw, dz rw, r w
-  b += 8.0 * 4.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);                // precond
-  b += 8.0 * 6.0 * nz;                                                   // pupdate (p = s, t = r)
+  b += 8.0 * 5.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);                // precond
+  b += 8.0 * (nc * nc + 3.0 * nc);                                       // coarse apply
+  b += 8.0 * 3.0 * nz;                                                   // pupdate (p = s)
   return b;
 }
 
@@ -279,11 +284,43 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.r, P.nz)
   DA(V.s, P.nz)
   DA(V.p, P.nz)
-  DA(V.t, P.nz)
   DA(V.ytmp, P.nz)
   DA(V.res, P.m)
   DA(V.u, P.m)
   DA(V.bdz, P.m)
+  DA(V.ctan, P.K)
+  DA(V.crad, P.K)
+  DA(P.rng_slot, 2 * (size_t)P.K)
+  // coarse level: free segment bases + landmarks of every instance (dense, when it fits shared memory)
+  {
+    h->c_off.assign(NI + 1, 0);
+    h->c_moff.assign(NI + 1, 0);
+    h->c_n.assign(NI, 0);
+    h->c_nb.assign(NI, 0);
+    long long moff = 0;
+    for (int i = 0; i < NI; ++i) {
+      const int nsegfree = h->seg_begin[i + 1] - h->seg_begin[i] - 1;
+      const int nb = nsegfree * (int)blk, nc = nb + (h->lm_off[i + 1] - h->lm_off[i]) * d;
+      const bool on = nc > 0 && nc <= kCoarseMax && coarse_smem_bytes(d, nc) <= 232448;
+      h->c_n[i] = on ? nc : 0;
+      h->c_nb[i] = on ? nb : 0;
+      h->c_off[i + 1] = h->c_off[i] + (on ? nc : 0);
+      moff += on ? (long long)nc * nc : 0;
+      if (moff >= (1ll << 31)) {
+        g_score_last_error = "coarse matrices too large for 32-bit indexing";
+        return SCORE_ERR_INVALID;
+      }
+      h->c_moff[i + 1] = (int)moff;
+      if (on && nc > h->c_nmax) h->c_nmax = nc;
+    }
+    if ((rc = upload(h, &P.c_off, h->c_off.data(), NI + 1))) return rc;
+    if ((rc = upload(h, &P.c_moff, h->c_moff.data(), NI + 1))) return rc;
+    if ((rc = upload(h, &P.c_n, h->c_n.data(), NI))) return rc;
+    if ((rc = upload(h, &P.c_nb, h->c_nb.data(), NI))) return rc;
+    DA(P.c_Ainv, (size_t)moff)
+    DA(P.c_rhs, h->c_off[NI])
+    DA(P.c_sol, h->c_off[NI])
+  }
   // block tables
   std::vector<BlockDesc> rb, cb;
   h->rb_begin.assign(NI + 1, 0);
@@ -348,7 +385,7 @@ extern "C" int score_create(const ScoreProblemDesc *desc, int32_t device, ScoreH
   return SCORE_OK;
 }
 
-constexpr int kKernelsPerTick = 8;
+constexpr int kKernelsPerTick = 11;
 
 // One solver tick.  `ev` (optional, kKernelsPerTick + 1 events) brackets every kernel for profiling.
 template <int D>
@@ -363,13 +400,20 @@ static void launch_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, 
   mark();
   k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
   mark();
-  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st);
+  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
   mark();
   k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
   mark();
+  if (h->c_nmax > 0)
+    k_coarse_build<D><<<P.n_inst, kCoarseThreads, coarse_smem_bytes_d<D>(h->c_nmax), st>>>(P, h->V, h->st, cfg.coarse_reg);
+  mark();
   k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
   mark();
-  k_precond<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
+  k_precond_rev<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
+  mark();
+  if (h->c_nmax > 0) k_coarse_apply<D><<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
+  mark();
+  k_precond_fwd<D><<<P.n_seg, kSegThreads, 0, st>>>(P, h->V, h->st);
   mark();
   k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone);
   mark();
@@ -385,11 +429,17 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   ScoreParams prm{};
   if (params) prm = *params;
   SolverCfg cfg;
-  cfg.max_newton = prm.max_newton > 0 ? prm.max_newton : 300;
+  cfg.max_newton = prm.max_newton > 0 ? prm.max_newton : 200;
   if (params && prm.max_newton == -1) cfg.max_newton = 0;  // "evaluate the start point only"
-  cfg.max_cg = prm.max_cg > 0 ? prm.max_cg : 300;
+  cfg.max_cg = prm.max_cg > 0 ? prm.max_cg : 100;
   cfg.kkt_tol = prm.kkt_tol > 0 ? prm.kkt_tol : 1e-6;
   cfg.forcing = prm.cg_forcing > 0 ? prm.cg_forcing : 0.1;
+  cfg.mu0 = prm.mu0 > 0 ? prm.mu0 : (prm.mu0 < 0 ? 0.0 : 1.0);
+  cfg.mu_factor = (prm.mu_factor > 0 && prm.mu_factor < 1) ? prm.mu_factor : 0.1;
+  cfg.center_tol = prm.center_tol > 0 ? prm.center_tol : 4.0;
+  cfg.mu_min = prm.mu_min > 0 ? prm.mu_min : 1e-16;
+  cfg.mu_eval = 1e-5;
+  cfg.coarse_reg = 1e-6;
   const int max_ticks = prm.max_ticks > 0 ? prm.max_ticks : 200000;
   const int tpl = prm.ticks_per_launch > 0 ? prm.ticks_per_launch : 32;
   SCORE_CUDA_CHECK(cudaSetDevice(h->device));
@@ -426,8 +476,16 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     k_build_M<<<grid_for(P.P, 128), 128, 0, st>>>(P, h->wsum);
     k_init_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z);
     k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
-    launches += 5;
-    for (double *v : {V.dz, V.r, V.s, V.p, V.t, V.ytmp})
+    if (P.K > 0) k_range_slots<<<grid_for(P.K, 256), 256, 0, st>>>(P);
+    launches += 6;
+    if (h->c_nmax > 0) {
+      const size_t smem = coarse_smem_bytes(d, h->c_nmax);
+      if (d == 2)
+        SCORE_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else
+        SCORE_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    for (double *v : {V.dz, V.r, V.s, V.p, V.ytmp})
       SCORE_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * P.nz, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.u, 0, sizeof(double) * P.m, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.bdz, 0, sizeof(double) * P.m, st));
@@ -438,6 +496,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       s.phase = PH_LS;
       s.skip_ls = 1;
       s.eta = cfg.forcing;
+      s.mu = s.mu_ls = cfg.mu0;
     }
     SCORE_CUDA_CHECK(cudaMemcpyAsync(h->st, init.data(), sizeof(InstState) * P.n_inst, cudaMemcpyHostToDevice, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(h->d_ndone, 0, sizeof(int), st));
@@ -465,7 +524,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     h->graph_cfg = cfg;
   }
   long ticks = 0;
-  double kernel_ms[kKernelsPerTick] = {0};
+  double kernel_ms[12] = {0};
   long profiled = 0;
   if (prm.profile_ticks > 0) {
     // un-graphed ticks with an event between every pair of kernels
@@ -525,8 +584,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     const double nnz_i = h->nnzoff[i + 1] - h->nnzoff[i], m_i = h->roff[i + 1] - h->roff[i];
     const double nz_i = h->zoff[i + 1] - h->zoff[i], K_i = h->rng_off[i + 1] - h->rng_off[i];
     const double P_i = h->pose_off[i + 1] - h->pose_off[i];
-    bytes += s.total_cg * bytes_cg_tick(d, nnz_i, m_i, nz_i, K_i, P_i) +
-             (s.newton_it + 1.0) * bytes_ls_tick(d, nnz_i, m_i, nz_i, K_i, P_i);
+    bytes += s.total_cg * bytes_cg_tick(d, nnz_i, m_i, nz_i, K_i, P_i, h->c_n[i]) +
+             (s.newton_it + 1.0) * bytes_ls_tick(d, nnz_i, m_i, nz_i, K_i, P_i, h->c_n[i]);
     if (inst_stats) {
       ScoreInstanceStats &o = inst_stats[i];
       o.solved = (s.phase == PH_DONE && s.solved) ? 1 : 0;
@@ -556,19 +615,23 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     stats->cols = P.nz;
     stats->algorithmic_bytes = bytes;
     stats->profiled_ticks = profiled;
-    for (int k = 0; k < kKernelsPerTick; ++k) stats->kernel_ms[k] = kernel_ms[k];
+    for (int k = 0; k < 12; ++k) stats->kernel_ms[k] = kernel_ms[k];
     // per-launch algorithmic bytes with every instance in the PCG phase
     const double nnz = P.nnz, m = P.m, nz = P.nz, K = P.K, Pn = P.P, blk = P.blk, d1 = d + 1;
-    const double nrb = h->T.n_rb, ncb = h->T.n_cb;
-    stats->kernel_bytes[0] = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 16.0 * m + 8.0 * (d * K + K);
-    stats->kernel_bytes[1] = 0.0;
-    stats->kernel_bytes[2] = 8.0 * nrb;
-    stats->kernel_bytes[3] = 0.0;
-    stats->kernel_bytes[4] = 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
-    stats->kernel_bytes[5] = 32.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);
-    stats->kernel_bytes[6] = 8.0 * (P.n_seg + P.n_inst);
-    stats->kernel_bytes[7] = 48.0 * nz;
-    (void)ncb;
+    double cmat = 0.0, cvec = 0.0;
+    for (int i = 0; i < P.n_inst; ++i) {
+      cmat += (double)h->c_n[i] * h->c_n[i];
+      cvec += h->c_n[i];
+    }
+    for (int k = 0; k < 12; ++k) stats->kernel_bytes[k] = 0.0;
+    stats->kernel_bytes[0] = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 16.0 * m + 8.0 * (d * K + 2.0 * K);  // rowpass
+    stats->kernel_bytes[2] = 8.0 * h->T.n_rb;                                                              // ctrl_a
+    stats->kernel_bytes[5] = 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;                            // colpass
+    stats->kernel_bytes[6] = 16.0 * nz + 8.0 * Pn * (blk + d1 * d1);                                       // precond_rev
+    stats->kernel_bytes[7] = 8.0 * (cmat + 3.0 * cvec);                                                    // coarse_apply
+    stats->kernel_bytes[8] = 24.0 * nz + 8.0 * Pn * blk;                                                   // precond_fwd
+    stats->kernel_bytes[9] = 8.0 * (P.n_seg + P.n_inst);                                                   // ctrl_b
+    stats->kernel_bytes[10] = 24.0 * nz;                                                                   // pupdate
   }
   for (auto &e : ev) cudaEventDestroy(e);
   return SCORE_OK;

@@ -14,7 +14,9 @@ constexpr int kRowsPerBlock = 768;  // divisible by 2 and 3 so a range's d rows 
 constexpr int kColsPerBlock = 768;
 constexpr int kThreads = 256;
 constexpr int kSegThreads = 128;  // chain-scan CTA width
-constexpr int kNumCand = 24;      // line-search candidates 2^(1 - c/2); slot kNumCand is a = 0
+constexpr int kNumCand = 12;      // line-search candidates 2^(1 - c/2); slot kNumCand is a = 0
+constexpr int kCoarseMax = 160;   // largest per-instance coarse space handled by the dense (shared-memory) solve
+constexpr int kCoarseThreads = 1024;
 constexpr int kLsSums = kNumCand + 1 + 3;
 
 enum Phase : int { PH_CG = 0, PH_LS = 1, PH_DONE = 2 };
@@ -30,8 +32,10 @@ struct BlockDesc {
 struct InstState {
   int phase, skip_ls, end_cg, solved;
   int newton_it, cg_it, total_cg, ls_fail;
-  double alpha, beta, rs, rs0, lam, eta, step;
-  double F, kkt, r_stat, r_gap, gnorm, xnorm, pt;
+  int eval_now, want_eval, n_eval, stall;  // true-KKT evaluation ticks
+  double alpha, beta, rs, rs0, eta, step;
+  double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
+  double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
 };
 
 struct DevProblem {
@@ -60,6 +64,12 @@ struct DevProblem {
   // odometry-chain preconditioner: G = dead-reckoned frame [Rg|tg] per pose (d x (d+1)),
   // M = G^-T D^-1 G^-1 per pose ((d+1) x (d+1)), landmark diagonal inverse
   double *G, *M, *lm_inv;
+  // coarse level (free segment bases + landmarks of an instance): slot of every range endpoint,
+  // per-instance offsets into the coarse vectors / matrices, size and on/off flag
+  int *rng_slot;                  // [2K] slot of endpoint a / b, -1 when it has no coarse dependence
+  int *c_off, *c_moff, *c_n, *c_nb;  // [n_inst(+1)]
+  double *c_Ainv;                 // per instance nc x nc inverse coarse Hessian
+  double *c_rhs, *c_sol;          // coarse right-hand side / solution
 };
 
 struct SolverVecs {
@@ -67,11 +77,12 @@ struct SolverVecs {
   double *z, *dz, *r, *s, *p, *t, *ytmp;
   // row space
   double *res, *u, *bdz;
+  double *ctan, *crad;  // [K] tangential / radial curvature factor of every range term at the current point
   // partial sums
   double *part_row;  // [n_row_blocks] pHp
   double *part_ls;   // [n_row_blocks * kLsSums]
   double *part_upd;  // [n_row_blocks * 2]  F, |delta|^2
-  double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2, p.t
+  double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2
   double *part_seg;  // [n_seg] r.s over chain segments
   double *part_lm;   // [n_inst] r.s over landmarks
 };
@@ -85,6 +96,7 @@ struct BlockTables {
 struct SolverCfg {
   int max_newton, max_cg;
   double kkt_tol, forcing;
+  double mu0, mu_factor, mu_min, mu_eval, center_tol, coarse_reg;
 };
 
 __host__ __device__ inline int find_inst(const int *off, int n_inst, int idx) {

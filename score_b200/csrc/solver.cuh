@@ -1,19 +1,22 @@
 // Solver tick kernels.
 //
-// The convex program the reference hands to Gurobi (score/solve_score.py:76; constraints
-// score/utils/gurobi_utils.py:316-352, objective :358-526) is solved here in its cone-eliminated form:
-// minimising over the auxiliary distance variable of each range (QCQP: delta in the unit ball,
-// SOCP: delta >= ||t_a - t_b||) leaves the smooth convex function
-//     F(z) = sum_edges w (B z)^2 + sum_ranges w max(0, ||t_a - t_b|| - r~)^2 + priors ,  z = (R, t, l),
-// with the pinned pose held fixed.  F is minimised by a semismooth Newton
-// method; every Newton system is solved by conjugate gradients preconditioned with the odometry
-// chain (precond.cuh), and a one-pass multi-candidate line search picks the step.
+// The convex program the reference hands to Gurobi's barrier (score/solve_score.py:76; constraints
+// score/utils/gurobi_utils.py:316-352, objective :358-526) is solved here by a primal interior-point
+// method in its cone-eliminated form.  For a barrier parameter mu the auxiliary distance variable of
+// every range is minimised out exactly (SURVEY.md App. A.4 is the mu = 0 case):
+//     phi_mu(n) = min_{0<=rho<1}  w (n - r rho)^2 - mu log(1 - rho^2),      n = ||t_a - t_b||,
+//     F_mu(z)   = sum_edges w (B z)^2 + sum_ranges phi_mu(||t_a - t_b||) + priors,   z = (R, t, l),
+// which is smooth and convex; its minimisers trace the central path of the log-barrier formulation of
+// the QCQP (ball constraint ||delta|| <= 1) — the same path an interior-point solver follows — and
+// F_0 is the reference objective with delta (QCQP) / the cone variable (SOCP) at their optimal values.
+// Each F_mu is minimised by Newton steps; every Newton system is solved by conjugate gradients with
+// the two-level preconditioner of precond.cuh, and a one-pass multi-candidate line search picks the
+// step.  mu shrinks whenever the Newton decrement says the iterate is centred.
 //
-// One "tick" = the fixed kernel sequence
-//     rowpass -> linesearch -> ctrl_a -> rowupdate -> colpass -> precond -> ctrl_b -> pupdate
-// Every instance of a batch advances by one operation per tick according to its own phase
-// (PH_CG: one PCG iteration; PH_LS: line search + gradient at the new point), so instances never
-// wait for each other.  All scalars live on the device; the host only replays a CUDA graph.
+// One "tick" is a fixed kernel sequence (api.cu: launch_tick).  Every instance of a batch advances by
+// one operation per tick according to its own phase (PH_CG: one PCG iteration; PH_LS: line search +
+// gradient at the new point; eval: certificate of the un-smoothed problem), so instances never wait
+// for each other.  All scalars live on the device; the host only replays a CUDA graph.
 #pragma once
 #include "common.cuh"
 
@@ -22,6 +25,60 @@ namespace score {
 __device__ __forceinline__ double ls_candidate(int c) {
   // 2^(1 - c/2), c = 0..kNumCand-1
   return ldexp((c & 1) ? 1.4142135623730951 : 1.0, 1 - (c + 1) / 2);
+}
+
+// eps = 1 - rho*, the root in (0,1] of (q - 1 + e) e (2 - e) = kap (1 - e)   (stationarity of phi_mu in rho
+// with q = n / r, kap = mu / (w r^2)); parametrised by eps so that rho -> 1 keeps full relative accuracy.
+__device__ __forceinline__ double barrier_eps(double q, double kap) {
+  const double qm = q - 1.0;
+  const double sq = sqrt(qm * qm + 2.0 * kap);
+  double e = (qm >= 0.0) ? kap / (qm + sq) : 0.5 * (sq - qm);
+  e = fmin(e, 1.0);
+  for (int it = 0; it < 6; ++it) {  // quadratic convergence; most ranges need 1-3 steps
+    const double F = (qm + e) * e * (2.0 - e) - kap * (1.0 - e);
+    const double dF = e * (2.0 - e) + (qm + e) * (2.0 - 2.0 * e) + kap;
+    double ne = e - F / dF;
+    if (!(ne > 0.0)) ne = 0.5 * e;
+    ne = fmin(ne, 1.0);
+    const bool done = fabs(ne - e) <= 2e-16 * e;
+    e = ne;
+    if (done) break;
+  }
+  return e;
+}
+
+// One range term at distance n: value phi_mu(n), tan = phi'/(2 w n), rad = phi''/(2 w).
+struct RangeTerm {
+  double val, tan, rad;
+};
+__device__ __forceinline__ RangeTerm range_term(double n, double r, double w, double mu, bool need_val) {
+  RangeTerm t;
+  if (!(r > 0.0)) {  // dist == 0: plain quadratic w n^2 (the delta column is all zeros)
+    t.val = w * n * n;
+    t.tan = 1.0;
+    t.rad = 1.0;
+    return t;
+  }
+  if (mu == 0.0) {  // exact elimination: w max(0, n - r)^2
+    const double e = n - r;
+    const bool act = e > 0.0;
+    t.val = act ? w * e * e : 0.0;
+    t.tan = act ? e / n : 0.0;
+    t.rad = act ? 1.0 : 0.0;
+    return t;
+  }
+  const double q = n / r, kap = mu / (w * r * r);
+  const double e = barrier_eps(q, kap);
+  const double rho = 1.0 - e, om = e * (2.0 - e);
+  const double c = kap * (1.0 + rho * rho) / (om * om);
+  t.rad = c / (1.0 + c);
+  t.tan = (q > 0.0) ? (q - 1.0 + e) / q : t.rad;
+  t.val = 0.0;
+  if (need_val) {
+    const double gap = r * (q - 1.0 + e);
+    t.val = w * gap * gap - mu * log(om);
+  }
+  return t;
 }
 
 // res = B z - b   (initialisation only)
@@ -33,15 +90,15 @@ __global__ void __launch_bounds__(kThreads) k_residual(DevProblem P, const doubl
   res[row] = acc;
 }
 
-// ---- K1: q = B x.  PH_CG: x = p, u = 2 W J q (J = generalised Jacobian of the per-range shrink at the
-// current residual), partial p'Hp.  PH_LS: x = dz, bdz = q.
+// ---- K1: q = B x.  PH_CG: x = p, u = 2 W H_r q (H_r = per-range curvature block tan I + (rad - tan) vv^T/n^2 of
+// F_mu at the current residual), partial p'Hp.  PH_LS: x = dz, bdz = q.
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
   __shared__ double sq[kRowsPerBlock];
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[blockIdx.x];
   const int phase = st[bd.inst].phase;
-  if (phase == PH_DONE) return;
+  if (phase == PH_DONE || st[bd.inst].eval_now) return;
   const double *__restrict__ x = (phase == PH_CG) ? V.p : V.dz;
   const int nrows = bd.i1 - bd.i0;
   for (int li = threadIdx.x; li < nrows; li += kThreads) {
@@ -66,7 +123,8 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
     double out = q;
     if (row >= rr0 && row < rr1) {
       const int rel = row - rr0, comp = rel % D, base = row - comp;
-      const double rr = P.rng_dist[P.rng_off[inst] + rel / D];
+      const int kk = P.rng_off[inst] + rel / D;
+      const double ct = V.ctan[kk], cr = V.crad[kk];
       double v[D], n2 = 0.0, dot = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
@@ -74,13 +132,8 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
         n2 += v[c] * v[c];
         dot += v[c] * sq[base - bd.i0 + c];
       }
-      const double nv = sqrt(n2);
-      if (nv > rr) {
-        const double inv = 1.0 / nv;
-        out = (1.0 - rr * inv) * q + (rr * inv) * (dot * inv) * (v[comp] * inv);
-      } else {
-        out = 0.0;
-      }
+      out = ct * q;
+      if (n2 > 0.0) out += (cr - ct) * (dot / n2) * v[comp];
     }
     const double u = 2.0 * P.w[row] * out;
     V.u[row] = u;
@@ -90,14 +143,15 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
   if (threadIdx.x == 0) V.part_row[blockIdx.x] = tot;
 }
 
-// ---- K_ls: phi(a) = F(res + a bdz) at kNumCand step sizes plus a = 0, in one pass.
+// ---- K_ls: F_mu(res + a bdz) at kNumCand step sizes plus a = 0, in one pass.
 // Plain rows are quadratic in a (three sums); range rows are evaluated per candidate.
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[blockIdx.x];
   const int inst = bd.inst;
-  if (st[inst].phase != PH_LS || st[inst].skip_ls) return;
+  if (st[inst].phase != PH_LS || st[inst].skip_ls || st[inst].eval_now) return;
+  const double mu = st[inst].mu;
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
   double sums[kLsSums];
@@ -122,11 +176,10 @@ __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVec
 #pragma unroll
       for (int c = 0; c < kNumCand; ++c) {
         const double a = ls_candidate(c);
-        const double e = fmax(0.0, sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C))) - rr);
-        sums[3 + c] += wk * e * e;
+        const double n = sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C)));
+        sums[3 + c] += range_term(n, rr, wk, mu, true).val;
       }
-      const double e0 = fmax(0.0, sqrt(A) - rr);
-      sums[3 + kNumCand] += wk * e0 * e0;
+      sums[3 + kNumCand] += range_term(sqrt(A), rr, wk, mu, true).val;
     } else {
       const double v = V.res[row], q = V.bdz[row], wr = P.w[row];
       sums[0] += wr * v * v;
@@ -148,22 +201,20 @@ __device__ __forceinline__ double ctrl_sum(const double *part, int i0, int i1, i
   return block_sum<kSegThreads>(acc, red);
 }
 
-// ---- ctrl_a: PCG step length / line-search decision.  One CTA per instance.
-__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st) {
+// ---- ctrl_a: PCG step length / line-search decision / barrier update.  One CTA per instance.
+__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg) {
   __shared__ double red[kSegThreads / 32];
   const int inst = blockIdx.x;
   InstState &S = st[inst];
   const int phase = S.phase;
-  if (phase == PH_DONE) return;
+  if (phase == PH_DONE || S.eval_now) return;
   const int b0 = T.rb_begin[inst], b1 = T.rb_begin[inst + 1];
   if (phase == PH_CG) {
-    double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0, red);
-    double pt = 0.0;
-    if (S.lam > 0.0) pt = ctrl_sum(V.part_col, T.cb_begin[inst], T.cb_begin[inst + 1], 4, 3, red);
+    const double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0, red);
     if (threadIdx.x == 0) {
-      pHp += S.lam * pt;
       if (pHp > 0.0 && pHp > 1e-30 * fabs(S.rs) && isfinite(pHp)) {
         S.alpha = S.rs / pHp;
+        S.dec += S.alpha * S.rs;  // -g.dz accumulates: Newton decrement^2 of the current solve
       } else {
         S.alpha = 0.0;
         S.end_cg = 1;
@@ -173,7 +224,10 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
   }
   // PH_LS
   if (S.skip_ls) {
-    if (threadIdx.x == 0) S.step = 0.0;
+    if (threadIdx.x == 0) {
+      S.step = 0.0;
+      S.mu_ls = S.mu;
+    }
     return;
   }
   double tot[kLsSums];
@@ -189,17 +243,34 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
       }
     }
     S.step = step;
+    S.mu_ls = S.mu;
+    // path following: once the Newton decrement (in units of mu) says the iterate is centred — or no
+    // candidate improved — the barrier parameter shrinks; the gradient of this tick already uses it
+    const double lam2 = (S.mu > 0.0) ? S.dec / S.mu : 0.0;
+    S.want_eval = 0;
+    if (S.mu > 0.0 && (lam2 <= cfg.center_tol || step == 0.0)) {
+      if (S.mu <= cfg.mu_eval) S.want_eval = 1;
+      if (S.mu <= cfg.mu_min) S.stall += 1;
+      S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
+    }
+    if (S.mu == 0.0) S.want_eval = 1;
+    // long late stages: look at the true certificate every 4th Newton step as well
+    if (S.mu <= cfg.mu_eval && (S.newton_it & 3) == 3) S.want_eval = 1;
+    if (step == 0.0) S.ls_fail += 1;
   }
 }
 
-// ---- K_upd (PH_LS): res += step * bdz ; u = y = 2 W shrink(res) ; partial F and |delta|^2.
+// ---- K_upd (PH_LS): res += step * bdz ; per-range curvature factors and u = dF_mu/d(res) ; partial F_mu.
+// Evaluation ticks (eval_now): u and sums of the un-smoothed problem (mu = 0) at the current point.
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[blockIdx.x];
   const int inst = bd.inst;
-  if (st[inst].phase != PH_LS) return;
-  const double step = st[inst].step;
+  const bool eval = st[inst].eval_now != 0;
+  if (st[inst].phase == PH_DONE || (st[inst].phase != PH_LS && !eval)) return;
+  const double step = eval ? 0.0 : st[inst].step;
+  const double mu = eval ? 0.0 : st[inst].mu;
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
   const int nrows = bd.i1 - bd.i0;
@@ -209,6 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
   int j = 0;
   for (int li = threadIdx.x; li < nrows; li += kThreads, ++j) {
     const int row = bd.i0 + li;
+    const double wr = P.w[row];
     double out;
     if (row >= rr0 && row < rr1) {
       const int rel = row - rr0, comp = rel % D, base = row - comp;
@@ -222,23 +294,30 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
       }
       newv[j] = v[comp];
       const double nv = sqrt(n2);
-      const double fac = (nv > rr) ? 1.0 - rr / nv : 0.0;
-      out = fac * v[comp];
-      if (comp == 0 && rr > 0.0) {
-        const double dn = fmin(1.0, nv / rr);
-        dacc += dn * dn;
+      const RangeTerm t = range_term(nv, rr, wr, mu, comp == 0);
+      out = t.tan * v[comp];
+      if (comp == 0) {
+        Facc += t.val;
+        if (!eval) {
+          V.ctan[k] = t.tan;
+          V.crad[k] = t.rad;
+        } else if (rr > 0.0) {
+          const double dn = fmin(1.0, nv / rr);
+          dacc += dn * dn;
+        }
       }
     } else {
       newv[j] = V.res[row] + step * V.bdz[row];
       out = newv[j];
+      Facc += wr * out * out;
     }
-    const double wr = P.w[row];
     V.u[row] = 2.0 * wr * out;
-    Facc += wr * out * out;
   }
   __syncthreads();
-  j = 0;
-  for (int li = threadIdx.x; li < nrows; li += kThreads, ++j) V.res[bd.i0 + li] = newv[j];
+  if (!eval) {
+    j = 0;
+    for (int li = threadIdx.x; li < nrows; li += kThreads, ++j) V.res[bd.i0 + li] = newv[j];
+  }
   const double Ftot = block_sum<kThreads>(Facc, red);
   const double dtot = block_sum<kThreads>(dacc, red);
   if (threadIdx.x == 0) {
@@ -247,31 +326,32 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
   }
 }
 
-// ---- K2: h = B^T u (+ lam t).  PH_CG: dz += alpha p, r -= alpha h.  PH_LS: z += step dz, dz = 0,
-// r = -h (h is the gradient at the new point), partial |g|^2, g.z, |z|^2.
+// ---- K2: h = B^T u.  PH_CG: dz += alpha p, r -= alpha h.  PH_LS: z += step dz, dz = 0, r = -h (h is the
+// gradient of F_mu at the new point).  Evaluation ticks: partial |g|^2, g.z, |z|^2 of the true gradient only.
 __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.cb[blockIdx.x];
   const int inst = bd.inst;
   const int phase = st[inst].phase;
   if (phase == PH_DONE) return;
-  const double alpha = st[inst].alpha, lam = st[inst].lam, step = st[inst].step;
+  const bool eval = st[inst].eval_now != 0;
+  const double alpha = st[inst].alpha, step = st[inst].step;
   const int pin_end = P.zoff[inst] + P.blk;
   double gg = 0.0, gz = 0.0, zz = 0.0;
   auto apply = [&](int col, double h) {
     if (col < pin_end) h = 0.0;
-    if (phase == PH_CG) {
-      if (lam > 0.0) h += lam * V.t[col];
+    if (eval) {
+      const double zc = V.z[col];
+      gg += h * h;
+      gz += h * zc;
+      zz += zc * zc;
+    } else if (phase == PH_CG) {
       V.dz[col] += alpha * V.p[col];
       V.r[col] -= alpha * h;
     } else {
-      const double zn = V.z[col] + step * V.dz[col];
-      V.z[col] = zn;
+      V.z[col] += step * V.dz[col];
       V.dz[col] = 0.0;
       V.r[col] = -h;
-      gg += h * h;
-      gz += h * zn;
-      zz += zn * zn;
     }
   };
   const int ncols = bd.i1 - bd.i0;
@@ -294,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V
       if (lane == 0) apply(col, h);
     }
   }
-  if (phase == PH_LS) {
+  if (eval) {
     const double a = block_sum<kThreads>(gg, red);
     const double b = block_sum<kThreads>(gz, red);
     const double c = block_sum<kThreads>(zz, red);
@@ -314,6 +394,33 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
   InstState &S = st[inst];
   const int phase = S.phase;
   if (phase == PH_DONE) return;
+  const int rb0 = T.rb_begin[inst], rb1 = T.rb_begin[inst + 1];
+  if (S.eval_now) {
+    // certificate of the un-smoothed problem with the auxiliary variables at their
+    // exact minimisers: r_link = 0, r_stat = |g_free| / (1 + |x|), p - D = g_free . z
+    const int cb0 = T.cb_begin[inst], cb1 = T.cb_begin[inst + 1];
+    const double F = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
+    const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 2, 1, red);
+    const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0, red);
+    const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1, red);
+    const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2, red);
+    if (threadIdx.x != 0) return;
+    S.F = F;
+    S.gnorm = sqrt(gg);
+    S.xnorm = sqrt(zz + dn2);
+    S.r_stat = S.gnorm / (1.0 + S.xnorm);
+    S.r_gap = fabs(gz) / (1.0 + fabs(F) + fabs(F - gz));
+    S.kkt = fmax(S.r_stat, S.r_gap);
+    S.n_eval += 1;
+    S.eval_now = 0;
+    const bool ok = S.kkt <= cfg.kkt_tol;
+    if (ok || S.newton_it >= cfg.max_newton || S.stall > 6 || !isfinite(F)) {
+      S.phase = PH_DONE;
+      S.solved = (ok && isfinite(F)) ? 1 : 0;
+      atomicAdd(n_done, 1);
+    }
+    return;
+  }
   double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
   if (phase == PH_CG) {
     if (threadIdx.x == 0) {
@@ -331,70 +438,31 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
     }
     return;
   }
-  // PH_LS: a new point (or the initial point) has just been evaluated
-  const int rb0 = T.rb_begin[inst], rb1 = T.rb_begin[inst + 1];
-  const int cb0 = T.cb_begin[inst], cb1 = T.cb_begin[inst + 1];
-  const double F = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
-  const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 2, 1, red);
-  const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0, red);
-  const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1, red);
-  const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2, red);
+  // PH_LS: a new point (or the initial point) has just been evaluated with barrier parameter S.mu
+  const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
   if (threadIdx.x != 0) return;
   rs_new += V.part_lm[inst];
-  // relative KKT of SURVEY.md App. A.7 with the auxiliary variables at their exact minimisers:
-  // r_link = 0, r_stat = |g_free| / (1 + |x|), p - D = g_free . z  =>  r_gap = |g.z| / (1 + |p| + |D|)
-  S.F = F;
-  S.gnorm = sqrt(gg);
-  S.xnorm = sqrt(zz + dn2);
-  S.r_stat = S.gnorm / (1.0 + S.xnorm);
-  S.r_gap = fabs(gz) / (1.0 + fabs(F) + fabs(F - gz));
-  S.kkt = fmax(S.r_stat, S.r_gap);
-  if (!S.skip_ls) {
-    S.newton_it += 1;
-    if (S.step == 0.0) {  // no candidate decreased F: damp the next Newton system
-      S.ls_fail += 1;
-      S.lam = fmax(S.lam, 1e-6) * 10.0;
-    } else if (S.step >= 0.99) {
-      S.lam = (S.lam < 1e-9) ? 0.0 : S.lam / 3.0;
-    } else if (S.step < 0.3) {
-      S.lam *= 3.0;
-    }
-  }
+  S.Fmu = Fmu;
+  if (!S.skip_ls) S.newton_it += 1;
   S.skip_ls = 0;
-  const bool ok = S.kkt <= cfg.kkt_tol || !(rs_new > 0.0);
-  if (ok || S.newton_it >= cfg.max_newton || S.ls_fail > 40 || !isfinite(F)) {
-    S.phase = PH_DONE;
-    S.solved = (ok && isfinite(F)) ? 1 : 0;
-    atomicAdd(n_done, 1);
-    return;
-  }
+  // start the next Newton solve
   S.phase = PH_CG;
   S.rs0 = S.rs = rs_new;
   S.beta = 0.0;
   S.cg_it = 0;
   S.end_cg = 0;
+  S.dec = 0.0;
   S.eta = cfg.forcing;
+  if (S.want_eval || !(rs_new > 0.0) || S.newton_it >= cfg.max_newton || !isfinite(Fmu)) S.eval_now = 1;
+  S.want_eval = 0;
 }
 
-// ---- K4 (PH_CG): p = s + beta p ; t = r + beta t  (t = P^{-1} p, used by the damping term) ; partial p.t
+// ---- K4 (PH_CG): p = s + beta p   (beta = 0 right after a Newton step; idempotent across an evaluation tick)
 __global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables T, const InstState *st) {
-  __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.cb[blockIdx.x];
   if (st[bd.inst].phase != PH_CG) return;
   const double beta = st[bd.inst].beta;
-  const bool need_pt = st[bd.inst].lam > 0.0;
-  double acc = 0.0;
-  for (int col = bd.i0 + threadIdx.x; col < bd.i1; col += kThreads) {
-    const double pn = V.s[col] + beta * V.p[col];
-    const double tn = V.r[col] + beta * V.t[col];
-    V.p[col] = pn;
-    V.t[col] = tn;
-    acc += pn * tn;
-  }
-  if (need_pt) {
-    const double tot = block_sum<kThreads>(acc, red);
-    if (threadIdx.x == 0) V.part_col[(size_t)blockIdx.x * 4 + 3] = tot;
-  }
+  for (int col = bd.i0 + threadIdx.x; col < bd.i1; col += kThreads) V.p[col] = V.s[col] + beta * V.p[col];
 }
 
 }  // namespace score

@@ -32,7 +32,8 @@ class SolveStats:
     kernel_bytes: Optional[np.ndarray] = None  # algorithmic bytes of one launch of each tick kernel
 
 
-KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_colpass", "k_precond", "k_ctrl_b", "k_pupdate"]
+KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_coarse_build", "k_colpass", "k_precond_rev",
+                "k_coarse_apply", "k_precond_fwd", "k_ctrl_b", "k_pupdate"]
 
 
 _INST_DTYPE = np.dtype(
@@ -123,6 +124,10 @@ class ScoreSolver:
         stream: int = 0,
         profile_ticks: int = 0,
         profile_skip: int = 0,
+        mu0: float = 0.0,
+        mu_factor: float = 0.0,
+        center_tol: float = 0.0,
+        mu_min: float = 0.0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
@@ -131,6 +136,7 @@ class ScoreSolver:
         prm.ticks_per_launch = ticks_per_launch
         prm.stream = C.c_void_p(stream) if stream else None
         prm.profile_ticks, prm.profile_skip = profile_ticks, profile_skip
+        prm.mu0, prm.mu_factor, prm.center_tol, prm.mu_min = mu0, mu_factor, center_tol, mu_min
         st = _lib.ScoreStats()
         inst = np.zeros(self.prob.n_instances, dtype=_INST_DTYPE)
         _check(self._lib.score_solve(self._h, C.byref(prm), C.byref(st),
@@ -138,8 +144,8 @@ class ScoreSolver:
         self.last_stats = SolveStats(
             st.n_instances, st.n_solved, st.ticks, st.kernel_launches, st.assemble_ms, st.setup_ms, st.solve_ms,
             st.extract_ms, st.total_ms, st.nnz_reduced, st.rows, st.cols, st.algorithmic_bytes, inst,
-            kernel_ms=np.array(st.kernel_ms[:]), profiled_ticks=int(st.profiled_ticks),
-            kernel_bytes=np.array(st.kernel_bytes[:]),
+            kernel_ms=np.array(st.kernel_ms[:len(KERNEL_NAMES)]), profiled_ticks=int(st.profiled_ticks),
+            kernel_bytes=np.array(st.kernel_bytes[:len(KERNEL_NAMES)]),
         )
         return self.last_stats
 

@@ -9,15 +9,16 @@ from score_b200.graph_io import load_graph_npz
 from score_b200.lowering import lower_factor_graph
 from score_b200.solver import ScoreSolver
 
+tol = float(os.environ.get("KKT", "1e-6"))
 names = sys.argv[1:] or ["mc0_small", "man1", "goats", "man4", "mc0"]
 for name in names:
     fg, extra = load_graph_npz(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     t0 = time.time()
     with ScoreSolver(lower_factor_graph(fg)) as s:
         t1 = time.time()
-        st = s.solve()
+        st = s.solve(kkt_tol=tol)
         t2 = time.time()
-        st2 = s.solve()
+        st2 = s.solve(kkt_tol=tol)
         poses, rounded, lms, dist = s.solution()
     rec = st.instances[0]
     print(f"{name}: solved={rec['solved']} f={rec['objective']:.9f} f*={float(extra['f_star']):.9f} kkt={rec['rel_kkt']:.3e} "
