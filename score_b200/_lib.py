@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libscore_b200.so")
 
 SCORE_RELAX_QCQP, SCORE_RELAX_SOCP = 0, 1
 SCORE_CSR_FULL, SCORE_CSR_REDUCED, SCORE_CSR_REDUCED_T = 0, 1, 2
+SCORE_OK, SCORE_ERR_INVALID, SCORE_ERR_CUDA, SCORE_ERR_STATE, SCORE_ERR_ALLOC = 0, -1, -2, -3, -4
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)

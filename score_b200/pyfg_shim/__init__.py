@@ -42,4 +42,8 @@ def install() -> bool:
     for sub in _SUBMODULES:
         mod = importlib.import_module(f"{__name__}.{sub}")
         sys.modules[f"py_factor_graph.{sub}"] = mod
+        # classes pickle under the real package's paths, so files written here load with PyFactorGraph
+        for obj in vars(mod).values():
+            if isinstance(obj, type) and obj.__module__ == mod.__name__:
+                obj.__module__ = f"py_factor_graph.{sub}"
     return True
