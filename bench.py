@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[3], the configuration "batched solves/sec" is qu
 the Monte-Carlo sweep of synthetic 20-robot x 100-pose 2D range-aided SLAM instances
 (score_b200/generators.py, seeds 20221003 + i), 1024 instances per GPU, QCQP relaxation,
 every instance solved to 1e-6 relative KKT.  One "step" = one full pass of the hot path over
-the batch: on-device assembly + preconditioner setup + semismooth Newton-PCG solve + SO(d)
+the batch: on-device assembly + preconditioner setup + interior-point Newton-PCG solve + SO(d)
 rounding.  With N GPUs every rank solves its own 1024 instances (no data-path collective; weak
 scaling); `value` is instances solved per second over all ranks.
 
@@ -310,6 +310,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     bytes_total = 0.0
     solve_ms = 0.0
     ticks = 0
+    cycles = 0
     n_solved = 0
     ev0.record()
     for _ in range(args.steps):
@@ -318,6 +319,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         bytes_total += st.algorithmic_bytes
         solve_ms += st.solve_ms
         ticks += st.ticks
+        cycles += st.cycles
         n_solved += st.n_solved
     ev1.record()
     barrier()
@@ -334,14 +336,18 @@ def run_gpu_arm(args, rank, local_rank, world):
     total_instances = args.instances * world * args.steps
     value = total_instances / (t_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: one extra step with CUDA events between the kernels of
-    # 32 early ticks (all instances still active), on the same stream
+    # ---- roofline of the dominant kernel
     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
         peak = float(json.load(f)["hbm_gbs"])
-    stp = solver.solve(kkt_tol=KKT_TOL, stream=stream, profile_ticks=32, profile_skip=8)
-    kms = stp.kernel_ms / max(1, stp.profiled_ticks)
-    dom = int(np.argmax(kms))
-    achieved = stp.kernel_bytes[dom] / (kms[dom] * 1e-3) / 1e9
+    # (a) whole solve, un-graphed, CUDA events between all kernels: time share of every kernel and its achieved
+    #     bandwidth over ALL its launches (partially filled late launches included)
+    stp = solver.solve(kkt_tol=KKT_TOL, stream=stream, profile_cycles=1 << 20, profile_skip=0)
+    # (b) four early cycles (every instance still active): per-launch figures at full occupancy
+    stf = solver.solve(kkt_tol=KKT_TOL, stream=stream, profile_cycles=4, profile_skip=2)
+    share = stp.kernel_ms / max(1e-12, stp.kernel_ms.sum())
+    dom = int(np.argmax(stp.kernel_ms))
+    cnt = np.maximum(1, stp.kernel_count)
+    achieved = stp.kernel_bytes_total[dom] / (stp.kernel_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -349,6 +355,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             traffic = json.load(open(tpath)).get(KERNEL_NAMES[dom])
         except (OSError, ValueError):
             traffic = None
+    full_ms = stf.kernel_ms / np.maximum(1, stf.kernel_count)
     roofline = {
         "bound": "hbm",
         "kernel": KERNEL_NAMES[dom],
@@ -358,14 +365,23 @@ def run_gpu_arm(args, rank, local_rank, world):
         "frac": achieved / peak,
         "traffic": traffic,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)",
-        "how": "CUDA events around every kernel of 32 un-graphed ticks (ticks 8..39, every instance active) in one extra "
-        "step on the solver stream; achieved = algorithmic bytes of one launch / mean launch time",
-        "ms_per_launch": float(kms[dom]),
-        "bytes_per_launch": float(stp.kernel_bytes[dom]),
-        "tick_kernel_ms": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
-        "tick_kernel_gbs": {
+        "how": "one extra step run un-graphed with a CUDA event between every pair of kernels on the solver stream; "
+        "dominant kernel = largest share of the step; achieved = algorithmic bytes summed over all its launches "
+        "(per-instance iteration counts x per-instance bytes, DESIGN.md) / summed launch time; traffic = ncu "
+        "dram bytes of one full-occupancy launch (profiles/traffic.json)",
+        "ms_per_launch": float(stp.kernel_ms[dom] / cnt[dom]),
+        "bytes_per_launch": float(stp.kernel_bytes_total[dom] / cnt[dom]),
+        "launches": int(stp.kernel_count[dom]),
+        "step_share": float(share[dom]),
+        "kernel_share_of_step": {n: float(v) for n, v in zip(KERNEL_NAMES, share)},
+        "kernel_gbs_whole_step": {
             n: (float(b / (v * 1e-3) / 1e9) if v > 0 and b > 0 else None)
-            for n, v, b in zip(KERNEL_NAMES, kms, stp.kernel_bytes)
+            for n, v, b in zip(KERNEL_NAMES, stp.kernel_ms, stp.kernel_bytes_total)
+        },
+        "kernel_ms_full_occupancy": {n: float(v) for n, v in zip(KERNEL_NAMES, full_ms)},
+        "kernel_gbs_full_occupancy": {
+            n: (float(b / (v * 1e-3) / 1e9) if v > 0 and b > 0 else None)
+            for n, v, b in zip(KERNEL_NAMES, full_ms, stf.kernel_bytes)
         },
         "whole_solve_gbs": bytes_total / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
     }
@@ -431,6 +447,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "solved": n_solved_all,
             "instances": total_instances,
             "ticks_per_step": ticks / args.steps,
+            "cycles_per_step": cycles / args.steps,
             "impl": "score_b200",
         }
         print(json.dumps(line), flush=True)

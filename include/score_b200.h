@@ -93,21 +93,25 @@ typedef struct {
 
 typedef struct {
   int32_t device;          /* CUDA device ordinal                                   */
-  int32_t max_newton;      /* outer (semismooth Newton) iteration cap, <=0: default  */
+  int32_t max_newton;      /* outer (Newton) iteration cap, <=0: default; -1: evaluate the start point only */
   int32_t max_cg;          /* inner PCG iteration cap per Newton step, <=0: default  */
   int32_t max_ticks;       /* global cap on solver ticks, <=0: default               */
   double kkt_tol;          /* relative KKT tolerance, <=0: 1e-6    */
   double cg_forcing;       /* inexact-Newton forcing term eta, <=0: 0.1              */
-  int32_t ticks_per_launch;/* ticks recorded per CUDA-graph replay, <=0: default     */
+  int32_t cg_per_cycle;    /* PCG ticks between two line-search ticks of the batch, <=0: default 3 */
   int32_t verbose;
   void *stream;            /* cudaStream_t to run on, NULL: library-owned stream     */
-  int32_t profile_ticks;   /* >0: time every kernel of this many early ticks with CUDA events (un-graphed) */
-  int32_t profile_skip;    /* ticks to run before the profiled ones                  */
+  int32_t profile_cycles;  /* >0: time every kernel of this many cycles with CUDA events (un-graphed) */
+  int32_t profile_skip;    /* cycles to run before the profiled ones                 */
   /* interior-point path following (0: defaults) */
   double mu0;              /* initial barrier parameter, default 1.0; < 0: no barrier (plain semismooth Newton) */
   double mu_factor;        /* barrier reduction per centred stage, default 0.1       */
   double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 4 */
   double mu_min;           /* smallest barrier parameter, default 1e-16              */
+  int32_t cg_grow_after;   /* from this cycle on the PCG ticks per cycle double every cg_grow_every cycles, <=0: never */
+  int32_t cg_grow_every;   /* <=0: 8                                                 */
+  int32_t coarse_every;    /* rebuild the coarse inverse every this many Newton steps of a barrier stage, <=0: 1 */
+  int32_t reserved1;
 } ScoreParams;
 
 /* Per-instance result record. */
@@ -122,18 +126,22 @@ typedef struct {
 
 typedef struct {
   int32_t n_instances, n_solved;
-  int64_t ticks;           /* solver ticks executed (each = one operator application per active instance) */
+  int64_t ticks;           /* solver ticks executed by the batch (line-search + PCG ticks)           */
+  int64_t cycles;          /* lockstep cycles (one line-search tick + evaluation tick + PCG ticks)   */
   int64_t kernel_launches; /* kernels launched by this call (incl. inside graphs)    */
   double assemble_ms, setup_ms, solve_ms, extract_ms, total_ms; /* CUDA-event times on the solver stream */
   int64_t nnz_reduced, rows, cols;  /* operator size over the batch                  */
-  double algorithmic_bytes;         /* sum over ticks of the bytes the active instances must move */
-  /* profile mode: summed CUDA-event time of each tick kernel over the profiled ticks, in launch order
+  double algorithmic_bytes;         /* bytes the instances had to move over the whole solve */
+  /* profile mode: summed CUDA-event time / launch count of each tick kernel over the profiled cycles; order
    * rowpass, linesearch, ctrl_a, rowupdate, coarse_build, colpass, precond_rev, coarse_apply, precond_fwd,
    * ctrl_b, pupdate */
   double kernel_ms[12];
-  int64_t profiled_ticks;
-  /* algorithmic bytes of ONE launch of each tick kernel with every instance in the PCG phase */
+  int64_t kernel_count[12];
+  int64_t profiled_cycles;
+  /* algorithmic bytes of ONE launch of each tick kernel with every instance active */
   double kernel_bytes[12];
+  /* algorithmic bytes of each tick kernel summed over the whole solve (per-instance iteration counts) */
+  double kernel_bytes_total[12];
 } ScoreStats;
 
 typedef struct ScoreHandle_ *ScoreHandle;
@@ -161,6 +169,14 @@ int score_get_solution(ScoreHandle h, double *pose_blocks, double *pose_rounded,
  * entries (only filled for SCORE_CSR_FULL / _REDUCED). */
 int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
                   int32_t *indptr, int32_t *indices, double *values, double *weights, double *rhs);
+
+/* Test / diagnostic access to solver internals of instance `inst` after score_solve (host buffer of
+ * `capacity` doubles; *count receives the number of doubles the array has; pass out = NULL to query):
+ *   SCORE_INT_COARSE_INV  nc x nc inverse coarse matrix of the last Newton step (0 doubles: coarse level off)
+ *   SCORE_INT_RANGE_CURV  K_inst x d(d+1)/2 curvature blocks 2 w H_k of the range terms (upper, row-major)
+ *   SCORE_INT_FRAMES      P_inst x d x (d+1) dead-reckoned frames of the odometry-chain preconditioner */
+enum { SCORE_INT_COARSE_INV = 0, SCORE_INT_RANGE_CURV = 1, SCORE_INT_FRAMES = 2 };
+int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, double *out, int64_t capacity, int64_t *count);
 
 /* Stand-alone SO(d) rounding of n d x d matrices (host pointers) on the device:
  * round_to_special_orthogonal, score/utils/matrix_utils.py:59-79. */

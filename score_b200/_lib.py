@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libscore_b200.so")
 
 SCORE_RELAX_QCQP, SCORE_RELAX_SOCP = 0, 1
 SCORE_CSR_FULL, SCORE_CSR_REDUCED, SCORE_CSR_REDUCED_T = 0, 1, 2
+SCORE_INT_COARSE_INV, SCORE_INT_RANGE_CURV, SCORE_INT_FRAMES = 0, 1, 2
 SCORE_OK, SCORE_ERR_INVALID, SCORE_ERR_CUDA, SCORE_ERR_STATE, SCORE_ERR_ALLOC = 0, -1, -2, -3, -4
 
 _i32p = C.POINTER(C.c_int32)
@@ -64,15 +65,19 @@ class ScoreParams(C.Structure):
         ("max_ticks", C.c_int32),
         ("kkt_tol", C.c_double),
         ("cg_forcing", C.c_double),
-        ("ticks_per_launch", C.c_int32),
+        ("cg_per_cycle", C.c_int32),
         ("verbose", C.c_int32),
         ("stream", C.c_void_p),
-        ("profile_ticks", C.c_int32),
+        ("profile_cycles", C.c_int32),
         ("profile_skip", C.c_int32),
         ("mu0", C.c_double),
         ("mu_factor", C.c_double),
         ("center_tol", C.c_double),
         ("mu_min", C.c_double),
+        ("cg_grow_after", C.c_int32),
+        ("cg_grow_every", C.c_int32),
+        ("coarse_every", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -94,6 +99,7 @@ class ScoreStats(C.Structure):
         ("n_instances", C.c_int32),
         ("n_solved", C.c_int32),
         ("ticks", C.c_int64),
+        ("cycles", C.c_int64),
         ("kernel_launches", C.c_int64),
         ("assemble_ms", C.c_double),
         ("setup_ms", C.c_double),
@@ -105,8 +111,10 @@ class ScoreStats(C.Structure):
         ("cols", C.c_int64),
         ("algorithmic_bytes", C.c_double),
         ("kernel_ms", C.c_double * 12),
-        ("profiled_ticks", C.c_int64),
+        ("kernel_count", C.c_int64 * 12),
+        ("profiled_cycles", C.c_int64),
         ("kernel_bytes", C.c_double * 12),
+        ("kernel_bytes_total", C.c_double * 12),
     ]
 
 
@@ -116,6 +124,7 @@ EXPORTED_SYMBOLS = [
     "score_get_sizes",
     "score_get_solution",
     "score_get_csr",
+    "score_get_internal",
     "score_round_so",
     "score_destroy",
     "score_last_error",
@@ -162,6 +171,8 @@ def load() -> C.CDLL:
         C.c_void_p,
     ]
     lib.score_get_csr.restype = C.c_int
+    lib.score_get_internal.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.score_get_internal.restype = C.c_int
     lib.score_round_so.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     lib.score_round_so.restype = C.c_int
     lib.score_destroy.argtypes = [C.c_void_p]

@@ -2,9 +2,12 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+#include <map>
 #include <vector>
 
 #include "assemble.cuh"
+#include "coarse.cuh"
 #include "common.cuh"
 #include "extract.cuh"
 #include "precond.cuh"
@@ -21,7 +24,9 @@ struct ScoreHandle_ {
   BlockTables T{};
   InstState *st = nullptr;
   int *d_ndone = nullptr;
-  int *h_ndone = nullptr;  // pinned
+  int *h_ndone = nullptr;  // pinned, two slots (double-buffered completion count)
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  std::map<int, cudaGraphExec_t> graphs;  // cycle length (PCG ticks) -> instantiated cycle graph
   double *wsum = nullptr;
   int *nnz_row = nullptr;
   // transpose scratch
@@ -37,12 +42,14 @@ struct ScoreHandle_ {
   int c_nmax = 0;
   std::vector<void *> allocs;
   cudaStream_t own_stream = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_ticks = 0;
   SolverCfg graph_cfg{};
   bool solved_once = false;
   int dist_per = 0;
 };
+
+constexpr int kNumKernels = 11;
+enum KernelId { KI_ROWPASS = 0, KI_LINESEARCH, KI_CTRL_A, KI_ROWUPDATE, KI_COARSE_BUILD, KI_COLPASS, KI_PRECOND_REV,
+                KI_COARSE_APPLY, KI_PRECOND_FWD, KI_CTRL_B, KI_PUPDATE };
 
 namespace {
 
@@ -92,29 +99,43 @@ int fetch_offsets(const int32_t *src, int n_inst, int64_t total, std::vector<int
 
 int grid_for(long n, int threads) { return (int)((n + threads - 1) / threads); }
 
-// Bytes one PCG tick of an instance must move (fp64 values, int32 indices; DESIGN.md "algorithmic bytes").
-double bytes_cg_tick(int d, double nnz, double m, double nz, double K, double Pn, double nc) {
-  const double blk = d * (d + 1), d1 = d + 1;
-  double b = 0.0;
-  b += 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * 2.0 * m + 8.0 * (d * K + 2.0 * K);  // rowpass
-  b += 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * 5.0 * nz;                            // colpass
-  b += 8.0 * 5.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);   // precond rev+fwd (r twice, ytmp w+r, s; G twice, M)
-  b += 8.0 * (nc * nc + 3.0 * nc);                           // coarse apply
-  b += 8.0 * 3.0 * nz;                                       // pupdate
-  return b;
-}
-double bytes_ls_tick(int d, double nnz, double m, double nz, double K, double Pn, double nc) {
-  const double blk = d * (d + 1), d1 = d + 1;
-  double b = 0.0;
-  b += 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * m;                  // rowpass: bdz = B dz
-  b += 8.0 * 2.0 * m + 8.0 * (m - d * K) + 16.0 * K;                     // linesearch: res, bdz, w(plain), r~, w(range)
-  b += 8.0 * 5.0 * m + 8.0 * 3.0 * K;                                    // rowupdate: res rw, bdz, w, u; r~, ctan, crad
-  b += 8.0 * (d * K + 6.0 * K) + 8.0 * nc * nc;                          // coarse build: res, factors, slots, G column; inverse out
-  b += 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * 5.0 * nz;           // colpass: z rw, dz rw, r w
-  b += 8.0 * 5.0 * nz + 8.0 * Pn * (2.0 * blk + d1 * d1);                // precond
-  b += 8.0 * (nc * nc + 3.0 * nc);                                       // coarse apply
-  b += 8.0 * 3.0 * nz;                                                   // pupdate (p = s)
-  return b;
+// Algorithmic bytes one instance moves through tick kernel `k` in tick mode `mode` (fp64 values, int32
+// indices, every array read or written once; DESIGN.md "algorithmic bytes").  Control kernels read a few
+// partial sums and are counted as zero.
+struct InstDims {
+  double d, nnz, m, nz, K, P, nc;
+};
+double kernel_bytes_inst(int k, int mode, const InstDims &D) {
+  const double d = D.d, blk = d * (d + 1), d1 = d + 1, nnz = D.nnz, m = D.m, nz = D.nz, K = D.K, Pn = D.P, nc = D.nc;
+  const bool cg = mode == TM_CG, ls = mode == TM_LS, ev = mode == TM_EVAL;
+  switch (k) {
+    case KI_ROWPASS:  // B (vals+cols+indptr), gather x; CG: w of the plain rows, u out, M_k of the ranges; LS: bdz out
+      if (cg) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * (m - d * K) + 8.0 * m + 8.0 * K * d * (d + 1) / 2;
+      if (ls) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * m;
+      return 0.0;
+    case KI_LINESEARCH:  // res, bdz, w of the plain rows, (dist, w) of the ranges
+      return ls ? 16.0 * m + 8.0 * (m - d * K) + 16.0 * K : 0.0;
+    case KI_ROWUPDATE:  // LS: res rw, bdz, w, u out, dist, M_k out; EVAL: res, w, u out, dist
+      if (ls) return 40.0 * m + 8.0 * K + 8.0 * K * d * (d + 1) / 2;
+      if (ev) return 24.0 * m + 8.0 * K;
+      return 0.0;
+    case KI_COARSE_BUILD:  // per incidence (2 K): code, 2w, frame, M_k; per pair entry (K): code, 2 frames, M_k; inverse out
+      return (ls && nc > 0) ? 2.0 * K * (12.0 + 8.0 * d1 + 4.0 * d * d1) + K * (4.0 + 16.0 * d1 + 4.0 * d * d1) + 8.0 * nc * nc
+                            : 0.0;
+    case KI_COLPASS:  // B^T, gather u; CG: dz rw, p, r rw; LS: z rw, dz rw, r out; EVAL: z
+      if (cg || ls) return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
+      return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * nz;
+    case KI_PRECOND_REV:  // r, ytmp out, G, M
+      return ev ? 0.0 : 16.0 * nz + 8.0 * Pn * (blk + d1 * d1);
+    case KI_COARSE_APPLY:
+      return ev ? 0.0 : 8.0 * (nc * nc + 3.0 * nc);
+    case KI_PRECOND_FWD:  // ytmp, r, s out, G
+      return ev ? 0.0 : 24.0 * nz + 8.0 * Pn * blk;
+    case KI_PUPDATE:  // s, p rw
+      return ev ? 0.0 : 24.0 * nz;
+    default:
+      return 0.0;
+  }
 }
 
 }  // namespace
@@ -125,12 +146,157 @@ extern "C" const char *score_version(void) { return "score_b200 0.1.0 (sm_100a)"
 extern "C" void score_destroy(ScoreHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto &e : h->ev_done)
+    if (e) cudaEventDestroy(e);
   for (void *p : h->allocs) cudaFree(p);
   if (h->sort_tmp) cudaFree(h->sort_tmp);
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
+}
+
+// Static sorted lists for the coarse-matrix build (coarse.cuh): per instance, the incidences (range,
+// endpoint) sorted by slot and the ranges sorted by (lower slot, higher slot), both by stable counting
+// sorts, the run tables, and the split of the off-diagonal runs over the 32 warps of the build CTA.
+static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
+  DevProblem &P = h->P;
+  const int NI = P.n_inst, blk = P.blk;
+  constexpr int NW = kCoarseThreads / 32;
+  std::vector<int> rng_a(P.K), rng_b(P.K), seg_ptr(P.n_seg + 1);
+  std::vector<double> rng_w(P.K);
+  if (P.K) {
+    SCORE_CUDA_CHECK(cudaMemcpy(rng_a.data(), desc->rng_a, sizeof(int) * P.K, cudaMemcpyDefault));
+    SCORE_CUDA_CHECK(cudaMemcpy(rng_b.data(), desc->rng_b, sizeof(int) * P.K, cudaMemcpyDefault));
+    SCORE_CUDA_CHECK(cudaMemcpy(rng_w.data(), desc->rng_w, sizeof(double) * P.K, cudaMemcpyDefault));
+  }
+  SCORE_CUDA_CHECK(cudaMemcpy(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1), cudaMemcpyDefault));
+  std::vector<int> inc_off(NI + 1, 0), inc_code, drun_off(NI + 1, 0), drun_slot, drun_begin;
+  std::vector<double> inc_w2;
+  std::vector<int> pr_off(NI + 1, 0), pr_code, orun_lo, orun_hi, orun_begin, owarp((size_t)NI * (NW + 1), 0);
+  inc_code.reserve(2 * (size_t)P.K);
+  inc_w2.reserve(2 * (size_t)P.K);
+  pr_code.reserve(P.K);
+  std::vector<int> pose_slot, cnt, pos, sa_v, sb_v;
+  for (int i = 0; i < NI; ++i) {
+    inc_off[i] = (int)inc_code.size();
+    pr_off[i] = (int)pr_code.size();
+    drun_off[i] = (int)drun_slot.size();
+    int *ws = &owarp[(size_t)i * (NW + 1)];
+    for (int w = 0; w <= NW; ++w) ws[w] = (int)orun_lo.size();
+    if (h->c_n[i] <= 0) continue;
+    const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
+    const int nsegfree = h->c_nb[i] / blk, nslots = nsegfree + Li;
+    const int k0 = h->rng_off[i], Ki = h->rng_off[i + 1] - k0;
+    pose_slot.assign(Pi, -1);
+    for (int s = h->seg_begin[i]; s < h->seg_begin[i + 1]; ++s)
+      for (int p = seg_ptr[s]; p < seg_ptr[s + 1]; ++p) pose_slot[p - h->pose_off[i]] = s - h->seg_begin[i] - 1;
+    auto slot_of = [&](int owner) { return owner < Pi ? pose_slot[owner] : nsegfree + (owner - Pi); };
+    sa_v.resize(Ki);
+    sb_v.resize(Ki);
+    // incidences by slot
+    cnt.assign(nslots + 1, 0);
+    for (int k = 0; k < Ki; ++k) {
+      const int a = rng_a[k0 + k], b = rng_b[k0 + k];
+      if (a < 0 || b < 0 || a >= Pi + Li || b >= Pi + Li) {
+        g_score_last_error = "range endpoint out of bounds";
+        return SCORE_ERR_INVALID;
+      }
+      const int sa = slot_of(a), sb = slot_of(b);
+      sa_v[k] = sa;
+      sb_v[k] = sb;
+      if (sa >= 0 && sa == sb) {
+        cnt[sa + 1]++;
+      } else {
+        if (sa >= 0) cnt[sa + 1]++;
+        if (sb >= 0) cnt[sb + 1]++;
+      }
+    }
+    for (int s = 0; s < nslots; ++s) cnt[s + 1] += cnt[s];
+    const int base = (int)inc_code.size(), ninc = cnt[nslots];
+    inc_code.resize(base + ninc);
+    inc_w2.resize(base + ninc);
+    for (int s = 0; s < nslots; ++s)
+      if (cnt[s + 1] > cnt[s]) {
+        drun_slot.push_back(s);
+        drun_begin.push_back(base + cnt[s]);
+      }
+    pos.assign(cnt.begin(), cnt.end() - 1);
+    auto put_inc = [&](int s, int k, int e) {
+      const int j = base + pos[s]++;
+      inc_code[j] = (k << 2) | e;
+      inc_w2[j] = 2.0 * rng_w[k0 + k];
+    };
+    for (int k = 0; k < Ki; ++k) {
+      const int sa = sa_v[k], sb = sb_v[k];
+      if (sa >= 0 && sa == sb) {
+        put_inc(sa, k, 2);
+      } else {
+        if (sa >= 0) put_inc(sa, k, 0);
+        if (sb >= 0) put_inc(sb, k, 1);
+      }
+    }
+    // ranges by slot pair
+    cnt.assign((size_t)nslots * nslots + 1, 0);
+    for (int k = 0; k < Ki; ++k) {
+      const int sa = sa_v[k], sb = sb_v[k];
+      if (sa < 0 || sb < 0 || sa == sb) continue;
+      cnt[(size_t)std::min(sa, sb) * nslots + std::max(sa, sb) + 1]++;
+    }
+    for (size_t q = 0; q < (size_t)nslots * nslots; ++q) cnt[q + 1] += cnt[q];
+    const int pbase = (int)pr_code.size(), npair = cnt[(size_t)nslots * nslots];
+    pr_code.resize(pbase + npair);
+    const int run0 = (int)orun_lo.size();
+    for (int lo = 0; lo < nslots; ++lo)
+      for (int hi = lo + 1; hi < nslots; ++hi) {
+        const size_t q = (size_t)lo * nslots + hi;
+        if (cnt[q + 1] > cnt[q]) {
+          orun_lo.push_back(lo);
+          orun_hi.push_back(hi);
+          orun_begin.push_back(pbase + cnt[q]);
+        }
+      }
+    pos.assign(cnt.begin(), cnt.end() - 1);
+    for (int k = 0; k < Ki; ++k) {
+      const int sa = sa_v[k], sb = sb_v[k];
+      if (sa < 0 || sb < 0 || sa == sb) continue;
+      const size_t q = (size_t)std::min(sa, sb) * nslots + std::max(sa, sb);
+      pr_code[pbase + pos[q]++] = (k << 1) | (sb < sa ? 1 : 0);
+    }
+    // contiguous, entry-balanced split of the off-diagonal runs over the warps
+    const int nrun = (int)orun_lo.size() - run0;
+    int w = 0;
+    for (int r = 0; r < nrun; ++r) {
+      const long long done = orun_begin[run0 + r] - pbase;
+      while (w < NW && done * NW >= (long long)(w + 1) * npair) ws[++w] = run0 + r;
+    }
+    while (w < NW) ws[++w] = run0 + nrun;
+    ws[0] = run0;
+  }
+  inc_off[NI] = (int)inc_code.size();
+  pr_off[NI] = (int)pr_code.size();
+  drun_off[NI] = (int)drun_slot.size();
+  drun_begin.push_back((int)inc_code.size());
+  orun_begin.push_back((int)pr_code.size());
+  P.c_ninc = (int)inc_code.size();
+  P.c_npair = (int)pr_code.size();
+  int rc;
+  const int d1 = P.d + 1;
+  if ((rc = upload(h, &P.c_inc_off, inc_off.data(), inc_off.size()))) return rc;
+  if ((rc = upload(h, &P.c_inc_code, inc_code.data(), inc_code.size()))) return rc;
+  if ((rc = upload(h, &P.c_inc_w2, inc_w2.data(), inc_w2.size()))) return rc;
+  if ((rc = upload(h, &P.c_drun_off, drun_off.data(), drun_off.size()))) return rc;
+  if ((rc = upload(h, &P.c_drun_slot, drun_slot.data(), drun_slot.size()))) return rc;
+  if ((rc = upload(h, &P.c_drun_begin, drun_begin.data(), drun_begin.size()))) return rc;
+  if ((rc = upload(h, &P.c_pr_off, pr_off.data(), pr_off.size()))) return rc;
+  if ((rc = upload(h, &P.c_pr_code, pr_code.data(), pr_code.size()))) return rc;
+  if ((rc = upload(h, &P.c_orun_lo, orun_lo.data(), orun_lo.size()))) return rc;
+  if ((rc = upload(h, &P.c_orun_hi, orun_hi.data(), orun_hi.size()))) return rc;
+  if ((rc = upload(h, &P.c_orun_begin, orun_begin.data(), orun_begin.size()))) return rc;
+  if ((rc = upload(h, &P.c_owarp, owarp.data(), owarp.size()))) return rc;
+  if ((rc = dalloc(h, &P.c_inc_h, (size_t)P.c_ninc * d1))) return rc;
+  if ((rc = dalloc(h, &P.c_pr_h, (size_t)P.c_npair * 2 * d1))) return rc;
+  return SCORE_OK;
 }
 
 static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle_ *h) {
@@ -288,9 +454,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.res, P.m)
   DA(V.u, P.m)
   DA(V.bdz, P.m)
-  DA(V.ctan, P.K)
-  DA(V.crad, P.K)
-  DA(P.rng_slot, 2 * (size_t)P.K)
+  DA(V.mk, (size_t)P.K * (d * (d + 1) / 2))
   // coarse level: free segment bases + landmarks of every instance (dense, when it fits shared memory)
   {
     h->c_off.assign(NI + 1, 0);
@@ -301,7 +465,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     for (int i = 0; i < NI; ++i) {
       const int nsegfree = h->seg_begin[i + 1] - h->seg_begin[i] - 1;
       const int nb = nsegfree * (int)blk, nc = nb + (h->lm_off[i + 1] - h->lm_off[i]) * d;
-      const bool on = nc > 0 && nc <= kCoarseMax && coarse_smem_bytes(d, nc) <= 232448;
+      const bool on = nc > 0 && nc <= kCoarseMax;
       h->c_n[i] = on ? nc : 0;
       h->c_nb[i] = on ? nb : 0;
       h->c_off[i + 1] = h->c_off[i] + (on ? nc : 0);
@@ -320,6 +484,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     DA(P.c_Ainv, (size_t)moff)
     DA(P.c_rhs, h->c_off[NI])
     DA(P.c_sol, h->c_off[NI])
+    if ((rc = build_coarse_tables(h, desc))) return rc;
   }
   // block tables
   std::vector<BlockDesc> rb, cb;
@@ -355,7 +520,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(h->out_round, (size_t)P.P * d * d)
   DA(h->out_dist, (size_t)P.K * h->dist_per)
 #undef DA
-  SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, sizeof(int)));
+  SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, 2 * sizeof(int)));
+  for (auto &e : h->ev_done) SCORE_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // radix-sort scratch for the transpose
   int end_bit = 1;
   while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
@@ -385,40 +551,171 @@ extern "C" int score_create(const ScoreProblemDesc *desc, int32_t device, ScoreH
   return SCORE_OK;
 }
 
-constexpr int kKernelsPerTick = 11;
 
-// One solver tick.  `ev` (optional, kKernelsPerTick + 1 events) brackets every kernel for profiling.
+// Optional per-kernel CUDA-event timing of un-graphed ticks (profile mode).
+struct TickProfiler {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ids;
+  cudaStream_t st;
+  void mark(int id) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    ids.push_back(id);
+  }
+  // call after the stream is synchronised
+  void collect(double *ms, long long *count) {
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+      if (ids[i] < 0) continue;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms[ids[i]] += t;
+      count[ids[i]] += 1;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    ev.clear();
+    ids.clear();
+  }
+};
+
+// Coarse build kernel for the handle's largest coarse space: tile size TS = ceil(nmax / 32).
+template <int D, int TS>
+static int coarse_build_attr(size_t smem) {
+  SCORE_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_build<D, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return SCORE_OK;
+}
+static int coarse_build_prepare(ScoreHandle_ *h) {
+  const int ts = coarse_tile_size(h->c_nmax), d = h->P.d;
+  const size_t smem = coarse_smem_bytes(d, ts);
+  switch (ts * 10 + d) {
+    case 12: return coarse_build_attr<2, 1>(smem);
+    case 22: return coarse_build_attr<2, 2>(smem);
+    case 32: return coarse_build_attr<2, 3>(smem);
+    case 42: return coarse_build_attr<2, 4>(smem);
+    case 13: return coarse_build_attr<3, 1>(smem);
+    case 23: return coarse_build_attr<3, 2>(smem);
+    case 33: return coarse_build_attr<3, 3>(smem);
+    case 43: return coarse_build_attr<3, 4>(smem);
+  }
+  g_score_last_error = "internal: unsupported coarse tile size";
+  return SCORE_ERR_STATE;
+}
 template <int D>
-static void launch_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st) {
   const DevProblem &P = h->P;
-  int k = 0;
-  auto mark = [&]() {
-    if (ev) cudaEventRecord(ev[k++], st);
-  };
-  mark();
-  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  mark();
-  k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  mark();
-  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
-  mark();
-  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  mark();
-  if (h->c_nmax > 0)
-    k_coarse_build<D><<<P.n_inst, kCoarseThreads, coarse_smem_bytes_d<D>(h->c_nmax), st>>>(P, h->V, h->st, cfg.coarse_reg);
-  mark();
-  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
-  mark();
+  const int ts = coarse_tile_size(h->c_nmax);
+  const size_t smem = coarse_smem_bytes_d<D>(ts);
+#define SCORE_CB(TS) \
+  k_coarse_build<D, TS><<<P.n_inst, kCoarseThreads, smem, st>>>(P, h->V, h->st, cfg.coarse_reg, cfg.coarse_every)
+  switch (ts) {
+    case 1: SCORE_CB(1); break;
+    case 2: SCORE_CB(2); break;
+    case 3: SCORE_CB(3); break;
+    default: SCORE_CB(4); break;
+  }
+#undef SCORE_CB
+}
+
+// Preconditioner application s = P r (+ partial r.s), shared by the line-search and PCG ticks.
+template <int D>
+static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
+  const DevProblem &P = h->P;
+  if (pf) pf->mark(KI_PRECOND_REV);
   k_precond_rev<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
-  mark();
-  if (h->c_nmax > 0) k_coarse_apply<D><<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
-  mark();
+  if (h->c_nmax > 0) {
+    if (pf) pf->mark(KI_COARSE_APPLY);
+    k_coarse_apply<D><<<P.n_inst, kCoarseApplyThreads, 0, st>>>(P, h->V, h->st);
+  }
+  if (pf) pf->mark(KI_PRECOND_FWD);
   k_precond_fwd<D><<<P.n_seg, kSegThreads, 0, st>>>(P, h->V, h->st);
-  mark();
-  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone);
-  mark();
+  return 2 + (h->c_nmax > 0 ? 1 : 0);
+}
+
+// Line-search tick: step along dz, new residual / gradient / curvature / coarse matrix, first preconditioned
+// residual of the next Newton system.  Returns the number of kernels launched.
+template <int D>
+static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
+  const DevProblem &P = h->P;
+  int n = 0;
+  if (pf) pf->mark(KI_ROWPASS);
+  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  if (pf) pf->mark(KI_LINESEARCH);
+  k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  if (pf) pf->mark(KI_CTRL_A);
+  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
+  if (pf) pf->mark(KI_ROWUPDATE);
+  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
+  n += 4;
+  if (h->c_nmax > 0) {
+    if (pf) pf->mark(KI_COARSE_BUILD);
+    launch_coarse_build<D>(h, cfg, st);
+    n += 1;
+  }
+  if (pf) pf->mark(KI_COLPASS);
+  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
+  n += 1 + launch_precond<D>(h, st, pf);
+  if (pf) pf->mark(KI_CTRL_B);
+  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS);
+  if (pf) pf->mark(KI_PUPDATE);
   k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
-  mark();
+  if (pf) pf->mark(-1);
+  return n + 2;
+}
+
+// Evaluation tick: certificate of the un-smoothed problem for the instances that asked for it.
+template <int D>
+static int launch_eval_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
+  const DevProblem &P = h->P;
+  if (pf) pf->mark(KI_ROWUPDATE);
+  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL);
+  if (pf) pf->mark(KI_COLPASS);
+  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL);
+  if (pf) pf->mark(KI_CTRL_B);
+  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL);
+  if (pf) pf->mark(-1);
+  return 3;
+}
+
+// PCG tick: one preconditioned conjugate-gradient iteration of every instance still solving its Newton system.
+template <int D>
+static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, bool last, TickProfiler *pf = nullptr) {
+  const DevProblem &P = h->P;
+  int n = 0;
+  if (pf) pf->mark(KI_ROWPASS);
+  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  if (pf) pf->mark(KI_CTRL_A);
+  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
+  if (pf) pf->mark(KI_COLPASS);
+  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_CG);
+  n += 3 + launch_precond<D>(h, st, pf);
+  if (pf) pf->mark(KI_CTRL_B);
+  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG);
+  if (pf) pf->mark(KI_PUPDATE);
+  k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
+  if (pf) pf->mark(-1);
+  return n + 2;
+}
+
+// One cycle = line-search tick + evaluation tick + n_cg PCG ticks.
+template <int D>
+static int launch_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr) {
+  int n = launch_ls_tick<D>(h, cfg, st, pf);
+  n += launch_eval_tick<D>(h, cfg, st, pf);
+  for (int i = 0; i < n_cg; ++i) n += launch_cg_tick<D>(h, cfg, st, i == n_cg - 1, pf);
+  return n;
+}
+static int launch_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr) {
+  return h->P.d == 2 ? launch_cycle<2>(h, cfg, st, n_cg, pf) : launch_cycle<3>(h, cfg, st, n_cg, pf);
+}
+
+// PCG ticks of cycle c: `base` early on, doubling every `grow_every` cycles after `grow_after` (the few
+// instances still running that late are the ill-conditioned ones that need longer inner solves).
+static int cycle_cg_ticks(int c, int base, int grow_after, int grow_every, int max_cg) {
+  if (c < grow_after) return base;
+  const int k = 1 + (c - grow_after) / grow_every;
+  long long n = (long long)base << std::min(k, 20);
+  return (int)std::min<long long>(n, max_cg);
 }
 
 extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats *stats, ScoreInstanceStats *inst_stats) {
@@ -428,7 +725,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   }
   ScoreParams prm{};
   if (params) prm = *params;
-  SolverCfg cfg;
+  SolverCfg cfg{};
   cfg.max_newton = prm.max_newton > 0 ? prm.max_newton : 200;
   if (params && prm.max_newton == -1) cfg.max_newton = 0;  // "evaluate the start point only"
   cfg.max_cg = prm.max_cg > 0 ? prm.max_cg : 100;
@@ -440,8 +737,10 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   cfg.mu_min = prm.mu_min > 0 ? prm.mu_min : 1e-16;
   cfg.mu_eval = 1e-5;
   cfg.coarse_reg = 1e-6;
+  cfg.coarse_every = prm.coarse_every > 0 ? prm.coarse_every : 1;
+  cfg.pad = 0;
   const int max_ticks = prm.max_ticks > 0 ? prm.max_ticks : 200000;
-  const int tpl = prm.ticks_per_launch > 0 ? prm.ticks_per_launch : 32;
+  int rc;
   SCORE_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t st = prm.stream ? (cudaStream_t)prm.stream : h->own_stream;
   DevProblem &P = h->P;
@@ -476,15 +775,14 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     k_build_M<<<grid_for(P.P, 128), 128, 0, st>>>(P, h->wsum);
     k_init_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z);
     k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
-    if (P.K > 0) k_range_slots<<<grid_for(P.K, 256), 256, 0, st>>>(P);
-    launches += 6;
-    if (h->c_nmax > 0) {
-      const size_t smem = coarse_smem_bytes(d, h->c_nmax);
+    if (h->c_nmax > 0 && std::max(P.c_ninc, P.c_npair) > 0) {
       if (d == 2)
-        SCORE_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_coarse_static<2><<<grid_for(std::max(P.c_ninc, P.c_npair), 256), 256, 0, st>>>(P);
       else
-        SCORE_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_coarse_static<3><<<grid_for(std::max(P.c_ninc, P.c_npair), 256), 256, 0, st>>>(P);
     }
+    launches += 6;
+    if (h->c_nmax > 0 && (rc = coarse_build_prepare(h))) return rc;
     for (double *v : {V.dz, V.r, V.s, V.p, V.ytmp})
       SCORE_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * P.nz, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.u, 0, sizeof(double) * P.m, st));
@@ -497,72 +795,78 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       s.skip_ls = 1;
       s.eta = cfg.forcing;
       s.mu = s.mu_ls = cfg.mu0;
+      s.mu_c = -1.0;
     }
     SCORE_CUDA_CHECK(cudaMemcpyAsync(h->st, init.data(), sizeof(InstState) * P.n_inst, cudaMemcpyHostToDevice, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(h->d_ndone, 0, sizeof(int), st));
     SCORE_CUDA_CHECK(cudaStreamSynchronize(st));  // init vector is on the host stack
   }
   SCORE_CUDA_CHECK(cudaEventRecord(ev[2], st));
-  // ---- 3. solver ticks (CUDA graph of `tpl` ticks, replayed until every instance is done)
-  if (h->graph_exec == nullptr || h->graph_ticks != tpl || memcmp(&h->graph_cfg, &cfg, sizeof(cfg)) != 0) {
-    if (h->graph_exec) {
-      cudaGraphExecDestroy(h->graph_exec);
-      h->graph_exec = nullptr;
-    }
-    cudaGraph_t graph;
-    SCORE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    for (int t = 0; t < tpl; ++t) {
-      if (d == 2)
-        launch_tick<2>(h, cfg, st);
-      else
-        launch_tick<3>(h, cfg, st);
-    }
-    SCORE_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-    SCORE_CUDA_CHECK(cudaGraphInstantiate(&h->graph_exec, graph, 0));
-    cudaGraphDestroy(graph);
-    h->graph_ticks = tpl;
+  // ---- 3. solver cycles (one CUDA graph per distinct cycle length, replayed until every instance is done)
+  if (memcmp(&h->graph_cfg, &cfg, sizeof(cfg)) != 0) {
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
     h->graph_cfg = cfg;
   }
-  long ticks = 0;
+  auto cycle_graph = [&](int n_cg, cudaGraphExec_t *out) -> int {
+    auto it = h->graphs.find(n_cg);
+    if (it != h->graphs.end()) {
+      *out = it->second;
+      return SCORE_OK;
+    }
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    SCORE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    launch_cycle_d(h, cfg, st, n_cg);
+    SCORE_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+    SCORE_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    h->graphs[n_cg] = exec;
+    *out = exec;
+    return SCORE_OK;
+  };
+  const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 3;
+  const int grow_after = prm.cg_grow_after > 0 ? prm.cg_grow_after : (1 << 30);
+  const int grow_every = prm.cg_grow_every > 0 ? prm.cg_grow_every : 8;
+  const int kernels_per_cg_tick = 7 + (h->c_nmax > 0 ? 1 : 0), kernels_per_ls_tick = 10 + (h->c_nmax > 0 ? 2 : 0) + 3;
+  long ticks = 0, cycles = 0;
   double kernel_ms[12] = {0};
+  long long kernel_count[12] = {0};
   long profiled = 0;
-  if (prm.profile_ticks > 0) {
-    // un-graphed ticks with an event between every pair of kernels
-    const int nskip = prm.profile_skip > 0 ? prm.profile_skip : 0, nprof = prm.profile_ticks;
-    for (int t = 0; t < nskip; ++t) {
-      if (d == 2)
-        launch_tick<2>(h, cfg, st);
-      else
-        launch_tick<3>(h, cfg, st);
-    }
-    std::vector<cudaEvent_t> pev((size_t)nprof * (kKernelsPerTick + 1));
-    for (auto &e : pev) SCORE_CUDA_CHECK(cudaEventCreate(&e));
-    for (int t = 0; t < nprof; ++t) {
-      if (d == 2)
-        launch_tick<2>(h, cfg, st, &pev[(size_t)t * (kKernelsPerTick + 1)]);
-      else
-        launch_tick<3>(h, cfg, st, &pev[(size_t)t * (kKernelsPerTick + 1)]);
-    }
-    SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
-    for (int t = 0; t < nprof; ++t)
-      for (int k = 0; k < kKernelsPerTick; ++k) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, pev[(size_t)t * (kKernelsPerTick + 1) + k], pev[(size_t)t * (kKernelsPerTick + 1) + k + 1]);
-        kernel_ms[k] += ms;
-      }
-    for (auto &e : pev) cudaEventDestroy(e);
-    ticks += nskip + nprof;
-    launches += (long)(nskip + nprof) * kKernelsPerTick;
-    profiled = nprof;
-  }
+  const int prof_skip = prm.profile_cycles > 0 ? std::max(0, prm.profile_skip) : 0;
+  const int prof_end = prm.profile_cycles > 0 ? prof_skip + prm.profile_cycles : 0;
+  TickProfiler pf;
+  pf.st = st;
+  h->h_ndone[0] = h->h_ndone[1] = 0;
   while (ticks < max_ticks) {
-    SCORE_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, st));
-    ticks += tpl;
-    launches += (long)tpl * kKernelsPerTick;
-    SCORE_CUDA_CHECK(cudaMemcpyAsync(h->h_ndone, h->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (*h->h_ndone >= P.n_inst) break;
+    const int n_cg = cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
+    const bool prof = cycles >= prof_skip && cycles < prof_end;
+    if (prof) {
+      launch_cycle_d(h, cfg, st, n_cg, &pf);
+      profiled += 1;
+    } else {
+      cudaGraphExec_t exec;
+      if ((rc = cycle_graph(n_cg, &exec))) return rc;
+      SCORE_CUDA_CHECK(cudaGraphLaunch(exec, st));
+    }
+    launches += kernels_per_ls_tick + (long)n_cg * kernels_per_cg_tick;
+    ticks += 1 + n_cg;
+    const int slot = (int)(cycles & 1);
+    SCORE_CUDA_CHECK(cudaMemcpyAsync(&h->h_ndone[slot], h->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCORE_CUDA_CHECK(cudaEventRecord(h->ev_done[slot], st));
+    cycles += 1;
+    // the completion count of the previous cycle is read while this one runs (no host bubble between cycles)
+    if (cycles >= 2) {
+      SCORE_CUDA_CHECK(cudaEventSynchronize(h->ev_done[slot ^ 1]));
+      if (h->h_ndone[slot ^ 1] >= P.n_inst) break;
+    }
+    if (prof && cycles == prof_end) {
+      SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+      pf.collect(kernel_ms, kernel_count);
+    }
   }
+  SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!pf.ev.empty()) pf.collect(kernel_ms, kernel_count);
   SCORE_CUDA_CHECK(cudaEventRecord(ev[3], st));
   // ---- 4. extraction
   k_split_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z, h->out_poses, h->out_lms);
@@ -577,15 +881,27 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   std::vector<InstState> fin(P.n_inst);
   SCORE_CUDA_CHECK(cudaMemcpy(fin.data(), h->st, sizeof(InstState) * P.n_inst, cudaMemcpyDeviceToHost));
   int n_solved = 0;
-  double bytes = 0.0;
+  double bytes = 0.0, kbytes_total[12] = {0}, kbytes_launch[12] = {0};
   for (int i = 0; i < P.n_inst; ++i) {
     const InstState &s = fin[i];
     n_solved += (s.phase == PH_DONE && s.solved) ? 1 : 0;
-    const double nnz_i = h->nnzoff[i + 1] - h->nnzoff[i], m_i = h->roff[i + 1] - h->roff[i];
-    const double nz_i = h->zoff[i + 1] - h->zoff[i], K_i = h->rng_off[i + 1] - h->rng_off[i];
-    const double P_i = h->pose_off[i + 1] - h->pose_off[i];
-    bytes += s.total_cg * bytes_cg_tick(d, nnz_i, m_i, nz_i, K_i, P_i, h->c_n[i]) +
-             (s.newton_it + 1.0) * bytes_ls_tick(d, nnz_i, m_i, nz_i, K_i, P_i, h->c_n[i]);
+    InstDims D;
+    D.d = d;
+    D.nnz = h->nnzoff[i + 1] - h->nnzoff[i];
+    D.m = h->roff[i + 1] - h->roff[i];
+    D.nz = h->zoff[i + 1] - h->zoff[i];
+    D.K = h->rng_off[i + 1] - h->rng_off[i];
+    D.P = h->pose_off[i + 1] - h->pose_off[i];
+    D.nc = h->c_n[i];
+    for (int k = 0; k < kNumKernels; ++k) {
+      const double bcg = kernel_bytes_inst(k, TM_CG, D), bls = kernel_bytes_inst(k, TM_LS, D);
+      // the first line-search tick only evaluates the start point (no direction yet)
+      const double n_ls = (k == KI_ROWPASS || k == KI_LINESEARCH) ? s.newton_it : s.newton_it + 1.0;
+      const double tot = s.total_cg * bcg + n_ls * bls + s.n_eval * kernel_bytes_inst(k, TM_EVAL, D);
+      kbytes_total[k] += tot;
+      bytes += tot;
+      kbytes_launch[k] += (bcg > 0.0) ? bcg : bls;
+    }
     if (inst_stats) {
       ScoreInstanceStats &o = inst_stats[i];
       o.solved = (s.phase == PH_DONE && s.solved) ? 1 : 0;
@@ -604,6 +920,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     stats->n_instances = P.n_inst;
     stats->n_solved = n_solved;
     stats->ticks = ticks;
+    stats->cycles = cycles;
     stats->kernel_launches = launches;
     stats->assemble_ms = ms[0];
     stats->setup_ms = ms[1];
@@ -614,24 +931,13 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     stats->rows = P.m;
     stats->cols = P.nz;
     stats->algorithmic_bytes = bytes;
-    stats->profiled_ticks = profiled;
-    for (int k = 0; k < 12; ++k) stats->kernel_ms[k] = kernel_ms[k];
-    // per-launch algorithmic bytes with every instance in the PCG phase
-    const double nnz = P.nnz, m = P.m, nz = P.nz, K = P.K, Pn = P.P, blk = P.blk, d1 = d + 1;
-    double cmat = 0.0, cvec = 0.0;
-    for (int i = 0; i < P.n_inst; ++i) {
-      cmat += (double)h->c_n[i] * h->c_n[i];
-      cvec += h->c_n[i];
+    stats->profiled_cycles = profiled;
+    for (int k = 0; k < 12; ++k) {
+      stats->kernel_ms[k] = kernel_ms[k];
+      stats->kernel_count[k] = kernel_count[k];
+      stats->kernel_bytes[k] = kbytes_launch[k];
+      stats->kernel_bytes_total[k] = kbytes_total[k];
     }
-    for (int k = 0; k < 12; ++k) stats->kernel_bytes[k] = 0.0;
-    stats->kernel_bytes[0] = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 16.0 * m + 8.0 * (d * K + 2.0 * K);  // rowpass
-    stats->kernel_bytes[2] = 8.0 * h->T.n_rb;                                                              // ctrl_a
-    stats->kernel_bytes[5] = 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;                            // colpass
-    stats->kernel_bytes[6] = 16.0 * nz + 8.0 * Pn * (blk + d1 * d1);                                       // precond_rev
-    stats->kernel_bytes[7] = 8.0 * (cmat + 3.0 * cvec);                                                    // coarse_apply
-    stats->kernel_bytes[8] = 24.0 * nz + 8.0 * Pn * blk;                                                   // precond_fwd
-    stats->kernel_bytes[9] = 8.0 * (P.n_seg + P.n_inst);                                                   // ctrl_b
-    stats->kernel_bytes[10] = 24.0 * nz;                                                                   // pupdate
   }
   for (auto &e : ev) cudaEventDestroy(e);
   return SCORE_OK;
@@ -761,6 +1067,52 @@ extern "C" int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t
     if (weights) SCORE_CUDA_CHECK(cudaMemcpy(weights, P.w + r0, sizeof(double) * rows, cudaMemcpyDefault));
     if (rhs) SCORE_CUDA_CHECK(cudaMemcpy(rhs, P.b + r0, sizeof(double) * rows, cudaMemcpyDefault));
   }
+  return SCORE_OK;
+}
+
+extern "C" int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, double *out, int64_t capacity,
+                                  int64_t *count) {
+  if (!h) {
+    g_score_last_error = "null handle";
+    return SCORE_ERR_INVALID;
+  }
+  const DevProblem &P = h->P;
+  if (inst < 0 || inst >= P.n_inst) {
+    g_score_last_error = "instance index out of range";
+    return SCORE_ERR_INVALID;
+  }
+  if (!h->solved_once) {
+    g_score_last_error = "solver internals exist only after score_solve";
+    return SCORE_ERR_STATE;
+  }
+  SCORE_CUDA_CHECK(cudaSetDevice(h->device));
+  const double *src = nullptr;
+  int64_t n = 0;
+  const int nm = P.d * (P.d + 1) / 2;
+  switch (which) {
+    case SCORE_INT_COARSE_INV:
+      n = (int64_t)h->c_n[inst] * h->c_n[inst];
+      src = P.c_Ainv + h->c_moff[inst];
+      break;
+    case SCORE_INT_RANGE_CURV:
+      n = (int64_t)(h->rng_off[inst + 1] - h->rng_off[inst]) * nm;
+      src = h->V.mk + (size_t)h->rng_off[inst] * nm;
+      break;
+    case SCORE_INT_FRAMES:
+      n = (int64_t)(h->pose_off[inst + 1] - h->pose_off[inst]) * P.blk;
+      src = P.G + (size_t)h->pose_off[inst] * P.blk;
+      break;
+    default:
+      g_score_last_error = "unknown internal array selector";
+      return SCORE_ERR_INVALID;
+  }
+  if (count) *count = n;
+  if (!out) return SCORE_OK;
+  if (capacity < n) {
+    g_score_last_error = "buffer too small";
+    return SCORE_ERR_INVALID;
+  }
+  if (n) SCORE_CUDA_CHECK(cudaMemcpy(out, src, sizeof(double) * n, cudaMemcpyDefault));
   return SCORE_OK;
 }
 

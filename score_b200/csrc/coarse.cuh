@@ -1,0 +1,425 @@
+// Coarse level of the preconditioner.
+//
+// The odometry Hessian is blind to two families of directions: rigid re-placement of a whole chain
+// segment (its base block U_first) and the landmarks.  Their curvature comes only from the range terms
+// and couples all segments of an instance.  Per instance these nc = (n_seg - 1) blk + L d coordinates
+// form a small dense block A_c = Z^T H_range Z (Z: tree coordinates -> x), rebuilt at every Newton step
+// from the current per-range curvature blocks M_k, inverted on chip, and applied inside the
+// preconditioner between the two prefix sums:  P = T blockdiag(D^-1, A_c^-1) T^T.
+//
+// A "slot" is one coarse block: free segment s (blk coordinates, the base frame of the segment) or
+// landmark q (d coordinates).  With h_p = (tg_p, 1) the dead-reckoned position of pose p in its segment
+// frame (landmarks: h = (0, 1)), J = I_d (x) h^T maps slot coordinates to the translation of an endpoint
+// and a range k between slots (a, b) contributes
+//     block(a, a) += M_k (x) h_a h_a^T        block(a, b) -= M_k (x) h_a h_b^T   (and transposed).
+// The contributions are summed from two static, host-sorted lists (api.cu: build_coarse_tables):
+//   * incidences sorted by slot      -> diagonal blocks, one warp per slot run;
+//   * ranges sorted by slot pair     -> upper off-diagonal blocks, contiguous runs per warp;
+// so every block has exactly one owning warp, the summation order is fixed and no atomics are needed.
+// The nc x nc matrix is then inverted by Gauss-Jordan elimination with the matrix held in registers
+// (TS x TS tile per thread; one pivot row / column broadcast through shared memory per step).
+#pragma once
+#include "common.cuh"
+
+namespace score {
+
+template <int D>
+struct CoarseDims {
+  static constexpr int D1 = D + 1;
+  static constexpr int BLK = D * D1;
+  static constexpr int NM = D * (D + 1) / 2;      // unique entries of the symmetric d x d curvature block
+  static constexpr int NH = D1 * (D1 + 1) / 2;    // unique entries of h h^T
+  static constexpr int NPD = NM * NH;             // products per incidence (diagonal blocks)
+  static constexpr int NPO = NM * D1 * D1;        // products per range (off-diagonal blocks)
+  static constexpr int SB = (D == 2) ? 32 : 16;   // ranges staged per warp batch
+  static constexpr int REC_D = NM + D1;           // staged doubles per incidence
+  static constexpr int REC_O = NM + 2 * D1;       // staged doubles per pair entry
+  static constexpr int STAGE = SB * REC_O;        // per-warp staging doubles
+};
+
+// (a, b) of the m-th unique entry of a symmetric D x D matrix stored row-major upper.
+template <int D>
+__host__ __device__ __forceinline__ void sym_pair(int m, int &a, int &b) {
+  a = 0;
+  int rowlen = D;
+  while (m >= rowlen) {
+    m -= rowlen;
+    ++a;
+    --rowlen;
+  }
+  b = a + m;
+}
+template <int D>
+__host__ __device__ __forceinline__ int sym_index(int a, int b) {
+  if (a > b) {
+    const int t = a;
+    a = b;
+    b = t;
+  }
+  return a * D - a * (a - 1) / 2 + (b - a);
+}
+
+// Static per-entry frames of the two sorted lists (after the dead reckoning): h of every incidence and of
+// both endpoints of every pair entry.
+template <int D>
+__global__ void k_coarse_static(DevProblem P) {
+  constexpr int D1 = D + 1, BLK = D * D1;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  auto frame = [&](int inst, int owner, double *h) {
+    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+    if (owner < Pi) {
+      const double *Gp = P.G + (size_t)(P.pose_off[inst] + owner) * BLK;
+#pragma unroll
+      for (int c = 0; c < D; ++c) h[c] = Gp[c * D1 + D];
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) h[c] = 0.0;
+    }
+    h[D] = 1.0;
+  };
+  if (j < P.c_ninc) {
+    const int inst = find_inst(P.c_inc_off, P.n_inst, j);
+    const int code = P.c_inc_code[j], k = P.rng_off[inst] + (code >> 2), e = code & 3;
+    double h[D1];
+    if (e == 2) {  // both endpoints in this slot: J_a - J_b
+      double hb[D1];
+      frame(inst, P.rng_a[k], h);
+      frame(inst, P.rng_b[k], hb);
+#pragma unroll
+      for (int c = 0; c < D1; ++c) h[c] -= hb[c];
+    } else {
+      frame(inst, e == 0 ? P.rng_a[k] : P.rng_b[k], h);
+    }
+#pragma unroll
+    for (int c = 0; c < D1; ++c) P.c_inc_h[(size_t)j * D1 + c] = h[c];
+  }
+  if (j < P.c_npair) {
+    const int inst = find_inst(P.c_pr_off, P.n_inst, j);
+    const int code = P.c_pr_code[j], k = P.rng_off[inst] + (code >> 1), flip = code & 1;
+    double ha[D1], hb[D1];
+    frame(inst, P.rng_a[k], ha);
+    frame(inst, P.rng_b[k], hb);
+#pragma unroll
+    for (int c = 0; c < D1; ++c) {
+      P.c_pr_h[(size_t)j * 2 * D1 + c] = flip ? hb[c] : ha[c];        // lower slot
+      P.c_pr_h[(size_t)j * 2 * D1 + D1 + c] = flip ? ha[c] : hb[c];   // higher slot
+    }
+  }
+}
+
+// coarse index of coordinate (r, c) of a slot; -1 when the slot has no such coordinate
+template <int D>
+__device__ __forceinline__ int coarse_index(int slot, int nsegfree, int nb, int r, int c) {
+  if (slot < nsegfree) return slot * (D * (D + 1)) + r * (D + 1) + c;
+  return (c == D) ? nb + (slot - nsegfree) * D + r : -1;
+}
+
+// Build + invert.  One CTA (1024 threads) per instance that is in a line-search tick.
+template <int D, int TS>
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, SolverVecs V, InstState *st, double reg,
+                                                                int every) {
+  using CD = CoarseDims<D>;
+  constexpr int D1 = CD::D1, BLK = CD::BLK, NM = CD::NM, NH = CD::NH, SB = CD::SB;
+  constexpr int NP = 32 * TS;  // padded matrix dimension
+  constexpr int NW = kCoarseThreads / 32;
+  extern __shared__ double sm[];
+  const int inst = blockIdx.x;
+  const int n = P.c_n[inst];
+  if (n <= 0 || n > NP || st[inst].phase != PH_LS || st[inst].eval_now) return;
+  // lagged coarse level: within one barrier stage the inverse is reused for `every` Newton steps
+  if (every > 1 && st[inst].mu == st[inst].mu_c && st[inst].c_age < every) {
+    __syncthreads();
+    if (threadIdx.x == 0) st[inst].c_age += 1;
+    return;
+  }
+  double *A = sm;                       // NP x NP
+  double *rowb = A + NP * NP;           // 2 x NP
+  double *colb = rowb + 2 * NP;         // 2 x NP
+  double *pivb = colb + 2 * NP;         // 2 (+2 pad)
+  double *stage = pivb + 4;             // NW x STAGE
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < NP * NP; i += kCoarseThreads) A[i] = 0.0;
+  __syncthreads();
+  const int nb = P.c_nb[inst], nsegfree = nb / BLK;
+  const int k0 = P.rng_off[inst];
+  double *mystage = stage + wid * CD::STAGE;
+
+  // ---- diagonal blocks: runs of the slot-sorted incidence list, run r -> warp r % NW
+  {
+    constexpr int NACC = (CD::NPD + 31) / 32;
+    int pm[NACC], pc[NACC], pcc[NACC];  // per accumulator: curvature entry, (c, c') of h h^T
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int p = lane + 32 * a;
+      pm[a] = (p < CD::NPD) ? p / NH : -1;
+      int c, cc;
+      sym_pair<D1>((p < CD::NPD) ? p % NH : 0, c, cc);
+      pc[a] = c;
+      pcc[a] = cc;
+    }
+    const int r0 = P.c_drun_off[inst], r1 = P.c_drun_off[inst + 1];
+    for (int run = r0 + wid; run < r1; run += NW) {
+      const int slot = P.c_drun_slot[run];
+      const int jb = P.c_drun_begin[run], je = P.c_drun_begin[run + 1];
+      double acc[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+      for (int j0 = jb; j0 < je; j0 += SB) {
+        const int cnt = min(SB, je - j0);
+        __syncwarp();
+        if (lane < cnt) {
+          const int j = j0 + lane;
+          const int k = k0 + (P.c_inc_code[j] >> 2);
+          const double w2r = reg * P.c_inc_w2[j];
+          double *rec = mystage + lane * CD::REC_D;
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            int a, b;
+            sym_pair<D>(m, a, b);
+            rec[m] = V.mk[(size_t)k * NM + m] + ((a == b) ? w2r : 0.0);
+          }
+#pragma unroll
+          for (int c = 0; c < D1; ++c) rec[NM + c] = P.c_inc_h[(size_t)j * D1 + c];
+        }
+        __syncwarp();
+        for (int q = 0; q < cnt; ++q) {
+          const double *rec = mystage + q * CD::REC_D;
+#pragma unroll
+          for (int a = 0; a < NACC; ++a)
+            if (pm[a] >= 0) acc[a] += rec[pm[a]] * (rec[NM + pc[a]] * rec[NM + pcc[a]]);
+        }
+      }
+      // flush: entry ((r, c), (r', c')) = M[r, r'] h[c] h[c'] and its symmetric images
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        if (pm[a] < 0) continue;
+        int r, rr;
+        sym_pair<D>(pm[a], r, rr);
+        const int c = pc[a], cc = pcc[a];
+        const int i0 = coarse_index<D>(slot, nsegfree, nb, r, c), i1 = coarse_index<D>(slot, nsegfree, nb, rr, cc);
+        const int i2 = coarse_index<D>(slot, nsegfree, nb, r, cc), i3 = coarse_index<D>(slot, nsegfree, nb, rr, c);
+        const double v = acc[a];
+        if (i0 >= 0 && i1 >= 0) {
+          A[i0 * NP + i1] += v;
+          if (i1 != i0) A[i1 * NP + i0] += v;
+        }
+        if (c != cc && r != rr && i2 >= 0 && i3 >= 0) {  // (r, c') x (r', c): distinct image only when both differ
+          A[i2 * NP + i3] += v;
+          A[i3 * NP + i2] += v;
+        }
+      }
+    }
+  }
+  // ---- upper off-diagonal blocks: contiguous runs of the pair-sorted range list per warp
+  {
+    constexpr int NACC = (CD::NPO + 31) / 32;
+    int pm[NACC], pc[NACC], pcc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int p = lane + 32 * a;
+      pm[a] = (p < CD::NPO) ? p / (D1 * D1) : -1;
+      pc[a] = (p / D1) % D1;
+      pcc[a] = p % D1;
+    }
+    const int *wsplit = P.c_owarp + (size_t)inst * (NW + 1);
+    const int run_b = wsplit[wid], run_e = wsplit[wid + 1];
+    for (int run = run_b; run < run_e; ++run) {
+      const int lo = P.c_orun_lo[run], hi = P.c_orun_hi[run];
+      const int jb = P.c_orun_begin[run], je = P.c_orun_begin[run + 1];
+      double acc[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+      for (int j0 = jb; j0 < je; j0 += SB) {
+        const int cnt = min(SB, je - j0);
+        __syncwarp();
+        if (lane < cnt) {
+          const int j = j0 + lane;
+          const int k = k0 + (P.c_pr_code[j] >> 1);
+          double *rec = mystage + lane * CD::REC_O;
+#pragma unroll
+          for (int m = 0; m < NM; ++m) rec[m] = V.mk[(size_t)k * NM + m];
+#pragma unroll
+          for (int c = 0; c < 2 * D1; ++c) rec[NM + c] = P.c_pr_h[(size_t)j * 2 * D1 + c];
+        }
+        __syncwarp();
+        for (int q = 0; q < cnt; ++q) {
+          const double *rec = mystage + q * CD::REC_O;
+#pragma unroll
+          for (int a = 0; a < NACC; ++a)
+            if (pm[a] >= 0) acc[a] += rec[pm[a]] * (rec[NM + pc[a]] * rec[NM + D1 + pcc[a]]);
+        }
+      }
+      // block(lo, hi)[(r, c), (r', c')] = -M[r, r'] h_lo[c] h_hi[c'];  M symmetric -> also (r', c), (r, c')
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        if (pm[a] < 0) continue;
+        int r, rr;
+        sym_pair<D>(pm[a], r, rr);
+        const int c = pc[a], cc = pcc[a];
+        const double v = -acc[a];
+        const int i0 = coarse_index<D>(lo, nsegfree, nb, r, c), i1 = coarse_index<D>(hi, nsegfree, nb, rr, cc);
+        if (i0 >= 0 && i1 >= 0) A[i0 * NP + i1] += v;
+        if (r != rr) {
+          const int i2 = coarse_index<D>(lo, nsegfree, nb, rr, c), i3 = coarse_index<D>(hi, nsegfree, nb, r, cc);
+          if (i2 >= 0 && i3 >= 0) A[i2 * NP + i3] += v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // landmark priors (w ||l - prior||^2) add 2 w on the diagonal
+  if (tid == 0) {
+    for (int pl = P.prior_off[inst]; pl < P.prior_off[inst + 1]; ++pl) {
+      const int q = P.prior_l[pl];
+      for (int r = 0; r < D; ++r) A[(nb + q * D + r) * NP + nb + q * D + r] += 2.0 * P.prior_w[pl];
+    }
+  }
+  __syncthreads();
+  // ---- load the register tile (mirroring the upper blocks), fix empty / padded coordinates
+  const int ty = wid, tx = lane;  // tile row / column
+  double Tl[TS][TS];
+#pragma unroll
+  for (int r = 0; r < TS; ++r)
+#pragma unroll
+    for (int c = 0; c < TS; ++c) {
+      const int i = ty * TS + r, j = tx * TS + c;
+      double v = (i <= j) ? A[i * NP + j] : A[j * NP + i];
+      if (i == j && (i >= n || !(v > 0.0))) v = 1.0;  // padding / coordinate without curvature: identity
+      Tl[r][c] = v;
+    }
+  // ---- in-place Gauss-Jordan inverse (SPD, no pivoting)
+  for (int k = 0; k < n; ++k) {
+    const int kt = k / TS, kl = k - kt * TS, buf = (k & 1) * NP;
+    if (ty == kt) {
+#pragma unroll
+      for (int r = 0; r < TS; ++r)
+        if (r == kl) {
+#pragma unroll
+          for (int c = 0; c < TS; ++c) rowb[buf + tx * TS + c] = Tl[r][c];
+        }
+    }
+    if (tx == kt) {
+#pragma unroll
+      for (int c = 0; c < TS; ++c)
+        if (c == kl) {
+#pragma unroll
+          for (int r = 0; r < TS; ++r) colb[buf + ty * TS + r] = Tl[r][c];
+          if (ty == kt) {
+#pragma unroll
+            for (int r = 0; r < TS; ++r)
+              if (r == kl) pivb[k & 1] = 1.0 / Tl[r][c];
+          }
+        }
+    }
+    __syncthreads();
+    const double inv = pivb[k & 1];
+    double rc[TS], cr[TS];
+#pragma unroll
+    for (int c = 0; c < TS; ++c) rc[c] = rowb[buf + tx * TS + c] * inv;
+#pragma unroll
+    for (int r = 0; r < TS; ++r) cr[r] = colb[buf + ty * TS + r];
+#pragma unroll
+    for (int r = 0; r < TS; ++r)
+#pragma unroll
+      for (int c = 0; c < TS; ++c) Tl[r][c] -= cr[r] * rc[c];
+    if (ty == kt) {  // pivot row: a_kj / p
+#pragma unroll
+      for (int r = 0; r < TS; ++r)
+        if (r == kl) {
+#pragma unroll
+          for (int c = 0; c < TS; ++c) Tl[r][c] = rc[c];
+        }
+    }
+    if (tx == kt) {  // pivot column: -a_ik / p ;  pivot: 1 / p
+#pragma unroll
+      for (int c = 0; c < TS; ++c)
+        if (c == kl) {
+#pragma unroll
+          for (int r = 0; r < TS; ++r) Tl[r][c] = -cr[r] * inv;
+          if (ty == kt) {
+#pragma unroll
+            for (int r = 0; r < TS; ++r)
+              if (r == kl) Tl[r][c] = inv;
+          }
+        }
+    }
+  }
+  // ---- write back, symmetrise, store
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < TS; ++r)
+#pragma unroll
+    for (int c = 0; c < TS; ++c) A[(ty * TS + r) * NP + tx * TS + c] = Tl[r][c];
+  __syncthreads();
+  double *out = P.c_Ainv + P.c_moff[inst];
+  for (int i = wid; i < n; i += NW)
+    for (int j = lane; j < n; j += 32) out[i * n + j] = 0.5 * (A[i * NP + j] + A[j * NP + i]);  // exactly symmetric
+  if (tid == 0) {
+    st[inst].mu_c = st[inst].mu;
+    st[inst].c_age = 1;
+  }
+}
+
+template <int D>
+inline size_t coarse_smem_bytes_d(int ts) {
+  const size_t np = 32 * (size_t)ts;
+  return sizeof(double) * (np * np + 4 * np + 4 + (size_t)(kCoarseThreads / 32) * CoarseDims<D>::STAGE);
+}
+inline size_t coarse_smem_bytes(int d, int ts) { return d == 2 ? coarse_smem_bytes_d<2>(ts) : coarse_smem_bytes_d<3>(ts); }
+inline int coarse_tile_size(int nmax) { return (nmax + 31) / 32; }
+
+// y = A_c^-1 c ;  scatter: segment bases -> ytmp (start value of the forward prefix sum), landmarks -> s.
+constexpr int kCoarseApplyThreads = 256;
+template <int D>
+__global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem P, SolverVecs V, const InstState *st) {
+  constexpr int BLK = D * (D + 1);
+  constexpr int NW = kCoarseApplyThreads / 32;
+  __shared__ double red[NW];
+  __shared__ double cs[kCoarseMax], ys[kCoarseMax];
+  const int inst = blockIdx.x;
+  const int n = P.c_n[inst];
+  if (n <= 0 || st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
+  const double *c = P.c_rhs + P.c_off[inst];
+  double *y = P.c_sol + P.c_off[inst];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n; i += kCoarseApplyThreads) cs[i] = c[i];
+  __syncthreads();
+  // two rows per warp step: all loads of both rows are issued before the reductions
+  for (int i = 2 * wid; i < n; i += 2 * NW) {
+    const bool two = i + 1 < n;
+    double a0 = 0.0, a1 = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const double cj = cs[j];
+      a0 += __ldg(Ai + (size_t)i * n + j) * cj;
+      if (two) a1 += __ldg(Ai + (size_t)(i + 1) * n + j) * cj;
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      ys[i] = a0;
+      if (two) ys[i + 1] = a1;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kCoarseApplyThreads) y[i] = ys[i];
+  const int nb = P.c_nb[inst];
+  const int seg0 = P.seg_begin[inst];
+  for (int i = threadIdx.x; i < nb; i += kCoarseApplyThreads) {
+    const int sl = i / BLK;
+    const int pg = P.seg_ptr[seg0 + 1 + sl];  // base pose of free segment sl
+    V.ytmp[P.zoff[inst] + (pg - P.pose_off[inst]) * BLK + (i % BLK)] = ys[i];
+  }
+  const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+  const int c0 = P.zoff[inst] + Pi * BLK;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < n - nb; j += kCoarseApplyThreads) {
+    const double sv = ys[nb + j];
+    V.s[c0 + j] = sv;
+    acc += sv * V.r[c0 + j];
+  }
+  const double tot = block_sum<kCoarseApplyThreads>(acc, red);
+  if (threadIdx.x == 0) V.part_lm[inst] = tot;
+}
+
+}  // namespace score

@@ -15,11 +15,15 @@ constexpr int kColsPerBlock = 768;
 constexpr int kThreads = 256;
 constexpr int kSegThreads = 128;  // chain-scan CTA width
 constexpr int kNumCand = 12;      // line-search candidates 2^(1 - c/2); slot kNumCand is a = 0
-constexpr int kCoarseMax = 160;   // largest per-instance coarse space handled by the dense (shared-memory) solve
+constexpr int kCoarseMax = 128;   // largest per-instance coarse space handled by the dense on-chip solve (4 x 4 register tiles)
 constexpr int kCoarseThreads = 1024;
 constexpr int kLsSums = kNumCand + 1 + 3;
 
-enum Phase : int { PH_CG = 0, PH_LS = 1, PH_DONE = 2 };
+// Per-instance phase.  PH_WAIT: this Newton system is solved to its forcing tolerance; idle until the
+// batch-wide line-search tick of the cycle.
+enum Phase : int { PH_CG = 0, PH_LS = 1, PH_DONE = 2, PH_WAIT = 3 };
+// Tick kind the host schedules (the same for every instance of the batch: the batch advances in lockstep).
+enum TickMode : int { TM_LS = 0, TM_EVAL = 1, TM_CG = 2, TM_CG_LAST = 3 };
 enum ColKind : int { CB_POSE = 0, CB_LANDMARK = 1 };
 
 // Work descriptor of one CTA of a row-pass / column-pass kernel.  A CTA never
@@ -34,6 +38,8 @@ struct InstState {
   int newton_it, cg_it, total_cg, ls_fail;
   int eval_now, want_eval, n_eval, stall;  // true-KKT evaluation ticks
   double alpha, beta, rs, rs0, eta, step;
+  int c_age, pad0;                         // Newton steps the current coarse inverse has served
+  double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
 };
@@ -66,7 +72,15 @@ struct DevProblem {
   double *G, *M, *lm_inv;
   // coarse level (free segment bases + landmarks of an instance): slot of every range endpoint,
   // per-instance offsets into the coarse vectors / matrices, size and on/off flag
-  int *rng_slot;                  // [2K] slot of endpoint a / b, -1 when it has no coarse dependence
+  // static sorted lists the coarse matrix is summed from (coarse.cuh)
+  int c_ninc, c_npair;
+  int *c_inc_off, *c_inc_code;       // [n_inst+1] ; [c_ninc] (local range << 2) | endpoint (0: a, 1: b, 2: a - b)
+  double *c_inc_h, *c_inc_w2;        // [c_ninc x (d+1)] frame of the endpoint ; [c_ninc] 2 w
+  int *c_drun_off, *c_drun_slot, *c_drun_begin;  // diagonal runs: [n_inst+1] ; [n_drun] ; [n_drun+1]
+  int *c_pr_off, *c_pr_code;         // [n_inst+1] ; [c_npair] (local range << 1) | (1: endpoint b is the lower slot)
+  double *c_pr_h;                    // [c_npair x 2 (d+1)] frames of the lower / higher slot endpoint
+  int *c_orun_lo, *c_orun_hi, *c_orun_begin;     // off-diagonal runs: [n_orun] x2 ; [n_orun+1]
+  int *c_owarp;                      // [n_inst x 33] first off-diagonal run of every warp of the build CTA
   int *c_off, *c_moff, *c_n, *c_nb;  // [n_inst(+1)]
   double *c_Ainv;                 // per instance nc x nc inverse coarse Hessian
   double *c_rhs, *c_sol;          // coarse right-hand side / solution
@@ -77,7 +91,7 @@ struct SolverVecs {
   double *z, *dz, *r, *s, *p, *t, *ytmp;
   // row space
   double *res, *u, *bdz;
-  double *ctan, *crad;  // [K] tangential / radial curvature factor of every range term at the current point
+  double *mk;  // [K x d(d+1)/2] curvature block 2 w (tan I + (rad - tan) v v^T / n^2) of every range term (upper, row-major)
   // partial sums
   double *part_row;  // [n_row_blocks] pHp
   double *part_ls;   // [n_row_blocks * kLsSums]
@@ -97,6 +111,7 @@ struct SolverCfg {
   int max_newton, max_cg;
   double kkt_tol, forcing;
   double mu0, mu_factor, mu_min, mu_eval, center_tol, coarse_reg;
+  int coarse_every, pad;
 };
 
 __host__ __device__ inline int find_inst(const int *off, int n_inst, int idx) {

@@ -216,230 +216,6 @@ __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], do
   if (threadIdx.x < NV) carry[threadIdx.x] = ncarry;
 }
 
-// ---- coarse level ---------------------------------------------------------------------------------
-// The odometry Hessian is blind to two families of directions: rigid re-placement of a whole chain
-// segment (its base block U_first) and the landmarks.  Their curvature comes only from the range terms
-// and couples all segments of an instance.  Per instance these nc = (n_seg - 1) blk + L d coordinates
-// form a small dense block A_c = Z^T H_range Z (Z: tree coordinates -> x), rebuilt at every Newton step
-// from the current per-range curvature factors, inverted in shared memory, and applied inside the
-// preconditioner between the two prefix sums:  P = T blockdiag(D^-1, A_c^-1) T^T.
-
-// slot (coarse block) of each range endpoint: free segment s -> s - 1 (segment 0 holds the pinned pose),
-// landmark q -> (n_seg_inst - 1) + q, pinned segment -> -1.
-__global__ void k_range_slots(DevProblem P) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.K) return;
-  const int inst = find_inst(P.rng_off, P.n_inst, k);
-  const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
-  const int nsegfree = P.seg_begin[inst + 1] - P.seg_begin[inst] - 1;
-  for (int e = 0; e < 2; ++e) {
-    const int o = e ? P.rng_b[k] : P.rng_a[k];
-    int slot;
-    if (o >= Pi) {
-      slot = nsegfree + (o - Pi);
-    } else {
-      const int seg = find_inst(P.seg_ptr, P.n_seg, P.pose_off[inst] + o);
-      slot = seg - P.seg_begin[inst] - 1;  // -1 for the pinned segment
-    }
-    P.rng_slot[2 * k + e] = slot;
-  }
-}
-
-// Assemble A_c in shared memory, invert it by Gauss-Jordan, write the inverse.  One CTA per instance
-// in PH_LS.  Range data is staged through shared memory in coalesced chunks; each warp owns the rows of
-// a subset of slots, so there are no atomics and the accumulation order is fixed.
-constexpr int kCoarseChunk = 512;
-template <int D>
-struct CoarseRange {  // one staged range
-  int slot[2];
-  double M[D][D];       // 2 w (tan' I + (rad - tan) v v^T / n^2)
-  double h[2][D + 1];   // (tg, 1) of the endpoint pose (segment slots only)
-};
-
-template <int D>
-__global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, SolverVecs V, const InstState *st,
-                                                                double reg) {
-  extern __shared__ double sm[];
-  constexpr int D1 = D + 1, BLK = D * D1;
-  const int inst = blockIdx.x;
-  const int n = P.c_n[inst];
-  if (n <= 0 || st[inst].phase != PH_LS || st[inst].eval_now) return;
-  double *A = sm;             // n x n
-  double *rowp = sm + n * n;  // n
-  double *colp = rowp + n;    // n
-  CoarseRange<D> *stage = reinterpret_cast<CoarseRange<D> *>(colp + n + (n & 1));
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = kCoarseThreads / 32;
-  for (int i = tid; i < n * n; i += kCoarseThreads) A[i] = 0.0;
-  const int nb = P.c_nb[inst], nsegfree = nb / BLK;
-  const int k0 = P.rng_off[inst], k1 = P.rng_off[inst + 1];
-  const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
-  for (int c0 = k0; c0 < k1; c0 += kCoarseChunk) {
-    __syncthreads();
-    const int cnt = min(kCoarseChunk, k1 - c0);
-    if (tid < cnt) {  // one thread stages one range (coalesced over k)
-      const int k = c0 + tid;
-      CoarseRange<D> &R = stage[tid];
-      const int sA = P.rng_slot[2 * k], sB = P.rng_slot[2 * k + 1];
-      R.slot[0] = sA;
-      R.slot[1] = sB;
-      const double w2 = 2.0 * P.rng_w[k];
-      const double ct = V.ctan[k], cr = V.crad[k];
-      double v[D], n2 = 0.0;
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        v[c] = V.res[rr0 + (k - k0) * D + c];
-        n2 += v[c] * v[c];
-      }
-      const double coef = (n2 > 0.0) ? (cr - ct) / n2 : 0.0;
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = 0; b < D; ++b) R.M[a][b] = w2 * (((a == b) ? ct + reg : 0.0) + coef * v[a] * v[b]);
-      const int own[2] = {P.rng_a[k], P.rng_b[k]};
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (R.slot[e] >= 0 && R.slot[e] < nsegfree) {
-          const double *Gp = P.G + (size_t)(P.pose_off[inst] + own[e]) * BLK;
-#pragma unroll
-          for (int c = 0; c < D; ++c) R.h[e][c] = Gp[c * D1 + D];
-          R.h[e][D] = 1.0;
-        }
-      }
-    }
-    __syncthreads();
-    for (int q = 0; q < cnt; ++q) {
-      const CoarseRange<D> &R = stage[q];
-      const int sA = R.slot[0], sB = R.slot[1];
-      const bool ownA = sA >= 0 && (sA % NW) == wid, ownB = sB >= 0 && (sB % NW) == wid;
-      if (!ownA && !ownB) continue;
-      int off[2], dim[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int sl = R.slot[e];
-        if (sl < 0) {
-          off[e] = 0;
-          dim[e] = 0;
-        } else if (sl < nsegfree) {
-          off[e] = sl * BLK;
-          dim[e] = BLK;
-        } else {
-          off[e] = nb + (sl - nsegfree) * D;
-          dim[e] = D;
-        }
-      }
-      // lane -> (row group, column): columns of both endpoint blocks side by side (<= 2 BLK <= 24)
-      const int ncols = dim[0] + dim[1];
-      const int cw = (ncols <= 16) ? 16 : 32, rstep = 32 / cw;
-      const int jj = lane % cw, ig = lane / cw;
-      if (jj < ncols) {
-        const int ec = (jj < dim[0]) ? 0 : 1;
-        const int j = (ec == 0) ? jj : jj - dim[0];
-        int rj = j;
-        double fj = 1.0;
-        if (dim[ec] == BLK) {
-          rj = j / D1;
-          fj = R.h[ec][j - rj * D1];
-        }
-#pragma unroll
-        for (int eo = 0; eo < 2; ++eo) {
-          if (!(eo == 0 ? ownA : ownB)) continue;
-          const double sgn = (eo == ec) ? fj : -fj;
-          for (int i = ig; i < dim[eo]; i += rstep) {
-            int ri = i;
-            double fi = 1.0;
-            if (dim[eo] == BLK) {
-              ri = i / D1;
-              fi = R.h[eo][i - ri * D1];
-            }
-            A[(off[eo] + i) * n + off[ec] + j] += sgn * fi * R.M[ri][rj];
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // landmark priors (w ||l - prior||^2) add 2 w on the diagonal
-  if (tid == 0) {
-    for (int pl = P.prior_off[inst]; pl < P.prior_off[inst + 1]; ++pl) {
-      const int q = P.prior_l[pl];
-      for (int r = 0; r < D; ++r) A[(nb + q * D + r) * n + nb + q * D + r] += 2.0 * P.prior_w[pl];
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += kCoarseThreads)
-    if (!(A[i * n + i] > 0.0)) A[i * n + i] = 1.0;  // coordinate without curvature: identity
-  __syncthreads();
-  // in-place Gauss-Jordan inverse (SPD, no pivoting): warps own rows, lanes sweep columns
-  for (int pv = 0; pv < n; ++pv) {
-    const double inv = 1.0 / A[pv * n + pv];
-    for (int i = tid; i < n; i += kCoarseThreads) {
-      rowp[i] = A[pv * n + i] * inv;
-      colp[i] = A[i * n + pv];
-    }
-    __syncthreads();
-    for (int i = wid; i < n; i += NW) {
-      double *Ai = A + i * n;
-      if (i == pv) {
-        for (int j = lane; j < n; j += 32) Ai[j] = (j == pv) ? inv : rowp[j];
-      } else {
-        const double ci = colp[i];
-        for (int j = lane; j < n; j += 32) Ai[j] = (j == pv) ? -ci * inv : Ai[j] - ci * rowp[j];
-      }
-    }
-    __syncthreads();
-  }
-  double *out = P.c_Ainv + P.c_moff[inst];
-  for (int i = wid; i < n; i += NW)
-    for (int j = lane; j < n; j += 32) out[i * n + j] = 0.5 * (A[i * n + j] + A[j * n + i]);  // exactly symmetric
-}
-
-template <int D>
-inline size_t coarse_smem_bytes_d(int nmax) {
-  return sizeof(double) * ((size_t)nmax * nmax + 2 * (size_t)nmax + 2) + sizeof(CoarseRange<D>) * kCoarseChunk;
-}
-inline size_t coarse_smem_bytes(int d, int nmax) {
-  return d == 2 ? coarse_smem_bytes_d<2>(nmax) : coarse_smem_bytes_d<3>(nmax);
-}
-
-// y = A_c^-1 c ;  scatter: segment bases -> ytmp (start value of the forward prefix sum), landmarks -> s.
-template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_coarse_apply(DevProblem P, SolverVecs V, const InstState *st) {
-  constexpr int BLK = D * (D + 1);
-  __shared__ double red[kSegThreads / 32];
-  const int inst = blockIdx.x;
-  const int n = P.c_n[inst];
-  if (n <= 0 || st[inst].phase == PH_DONE || st[inst].eval_now) return;
-  const double *Ai = P.c_Ainv + P.c_moff[inst];
-  const double *c = P.c_rhs + P.c_off[inst];
-  double *y = P.c_sol + P.c_off[inst];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = wid; i < n; i += kSegThreads / 32) {
-    double acc = 0.0;
-    for (int j = lane; j < n; j += 32) acc += Ai[(size_t)i * n + j] * c[j];
-    acc = warp_sum(acc);
-    if (lane == 0) y[i] = acc;
-  }
-  __syncthreads();
-  const int nb = P.c_nb[inst];
-  const int seg0 = P.seg_begin[inst];
-  for (int i = threadIdx.x; i < nb; i += kSegThreads) {
-    const int sl = i / BLK;
-    const int pg = P.seg_ptr[seg0 + 1 + sl];  // base pose of free segment sl
-    V.ytmp[P.zoff[inst] + (pg - P.pose_off[inst]) * BLK + (i % BLK)] = y[i];
-  }
-  const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
-  const int c0 = P.zoff[inst] + Pi * BLK;
-  double acc = 0.0;
-  for (int j = threadIdx.x; j < n - nb; j += kSegThreads) {
-    const double sv = y[nb + j];
-    V.s[c0 + j] = sv;
-    acc += sv * V.r[c0 + j];
-  }
-  const double tot = block_sum<kSegThreads>(acc, red);
-  if (threadIdx.x == 0) V.part_lm[inst] = tot;
-}
-
 // ---- s = P r, pass 1 (reverse): S_p = sum_{q>=p} r_q G_q^T ;  Y_p = S_p M_p -> ytmp.
 // With the coarse level on, the base block S_first goes to the coarse right-hand side instead.
 // CTA per chain segment; CTAs past n_seg handle the landmark block of one instance each.
@@ -453,7 +229,7 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, Solve
   int s = blockIdx.x;
   if (s >= P.n_seg) {
     const int inst = s - P.n_seg;
-    if (st[inst].phase == PH_DONE || st[inst].eval_now) return;
+    if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
     const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
     const int n = (P.lm_off[inst + 1] - P.lm_off[inst]) * D;
     const int c0 = P.zoff[inst] + Pi * P.blk, j0 = P.lm_off[inst] * D;
@@ -474,7 +250,7 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, Solve
     return;
   }
   const int inst = P.seg_inst[s];
-  if (st[inst].phase == PH_DONE || st[inst].eval_now) return;
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
   const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
   const int slot = s - P.seg_begin[inst] - 1;  // -1: pinned segment
@@ -546,7 +322,7 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, Solve
   const int tid = threadIdx.x;
   const int s = blockIdx.x;
   const int inst = P.seg_inst[s];
-  if (st[inst].phase == PH_DONE || st[inst].eval_now) return;
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
   const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
   if (tid < NV) carry[tid] = 0.0;

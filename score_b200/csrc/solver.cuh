@@ -13,10 +13,13 @@
 // the two-level preconditioner of precond.cuh, and a one-pass multi-candidate line search picks the
 // step.  mu shrinks whenever the Newton decrement says the iterate is centred.
 //
-// One "tick" is a fixed kernel sequence (api.cu: launch_tick).  Every instance of a batch advances by
-// one operation per tick according to its own phase (PH_CG: one PCG iteration; PH_LS: line search +
-// gradient at the new point; eval: certificate of the un-smoothed problem), so instances never wait
-// for each other.  All scalars live on the device; the host only replays a CUDA graph.
+// The batch advances in lockstep cycles scheduled by the host (api.cu): one line-search tick (TM_LS: step
+// along the Newton direction, gradient + curvature + coarse matrix at the new point), one evaluation tick
+// (TM_EVAL: certificate of the un-smoothed problem, only for instances that asked for it) and n_cg PCG ticks
+// (TM_CG).  An instance whose PCG reaches its forcing tolerance idles (PH_WAIT) until the next line-search
+// tick; one whose PCG needs longer simply keeps iterating through it (the line-search tick's kernel sequence
+// contains the PCG one) and takes a later opportunity.  The expensive line-search kernels therefore run only
+// once per cycle, at high batch occupancy, and PCG ticks launch nothing else.  All scalars live on the device; the host only replays CUDA graphs of whole cycles.
 #pragma once
 #include "common.cuh"
 
@@ -91,14 +94,15 @@ __global__ void __launch_bounds__(kThreads) k_residual(DevProblem P, const doubl
 }
 
 // ---- K1: q = B x.  PH_CG: x = p, u = 2 W H_r q (H_r = per-range curvature block tan I + (rad - tan) vv^T/n^2 of
-// F_mu at the current residual), partial p'Hp.  PH_LS: x = dz, bdz = q.
+// F_mu at the current residual, stored as M_k = 2 w H_r by k_rowupdate), partial p'Hp.  PH_LS: x = dz, bdz = q.
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
   __shared__ double sq[kRowsPerBlock];
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[blockIdx.x];
   const int phase = st[bd.inst].phase;
-  if (phase == PH_DONE || st[bd.inst].eval_now) return;
+  if ((phase != PH_CG && phase != PH_LS) || st[bd.inst].eval_now) return;
+  if (phase == PH_LS && st[bd.inst].skip_ls) return;  // start point: no direction yet (bdz stays 0)
   const double *__restrict__ x = (phase == PH_CG) ? V.p : V.dz;
   const int nrows = bd.i1 - bd.i0;
   for (int li = threadIdx.x; li < nrows; li += kThreads) {
@@ -120,22 +124,20 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
   for (int li = threadIdx.x; li < nrows; li += kThreads) {
     const int row = bd.i0 + li;
     const double q = sq[li];
-    double out = q;
+    double u;
     if (row >= rr0 && row < rr1) {
-      const int rel = row - rr0, comp = rel % D, base = row - comp;
-      const int kk = P.rng_off[inst] + rel / D;
-      const double ct = V.ctan[kk], cr = V.crad[kk];
-      double v[D], n2 = 0.0, dot = 0.0;
+      // range rows: u = M_k q  (M_k already carries 2 w)
+      const int rel = row - rr0, comp = rel % D, base = row - comp - bd.i0;
+      const double *mk = V.mk + (size_t)(P.rng_off[inst] + rel / D) * (D * (D + 1) / 2);
+      u = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        v[c] = V.res[base + c];
-        n2 += v[c] * v[c];
-        dot += v[c] * sq[base - bd.i0 + c];
+        const int a = comp < c ? comp : c, b = comp < c ? c : comp;
+        u += mk[a * D - a * (a - 1) / 2 + (b - a)] * sq[base + c];
       }
-      out = ct * q;
-      if (n2 > 0.0) out += (cr - ct) * (dot / n2) * v[comp];
+    } else {
+      u = 2.0 * P.w[row] * q;
     }
-    const double u = 2.0 * P.w[row] * out;
     V.u[row] = u;
     acc += q * u;
   }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
   const int inst = blockIdx.x;
   InstState &S = st[inst];
   const int phase = S.phase;
-  if (phase == PH_DONE || S.eval_now) return;
+  if ((phase != PH_CG && phase != PH_LS) || S.eval_now) return;
   const int b0 = T.rb_begin[inst], b1 = T.rb_begin[inst + 1];
   if (phase == PH_CG) {
     const double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0, red);
@@ -263,12 +265,14 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
 // ---- K_upd (PH_LS): res += step * bdz ; per-range curvature factors and u = dF_mu/d(res) ; partial F_mu.
 // Evaluation ticks (eval_now): u and sums of the un-smoothed problem (mu = 0) at the current point.
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
+__global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                        int mode) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[blockIdx.x];
   const int inst = bd.inst;
-  const bool eval = st[inst].eval_now != 0;
-  if (st[inst].phase == PH_DONE || (st[inst].phase != PH_LS && !eval)) return;
+  const bool eval = mode == TM_EVAL;
+  if (st[inst].phase == PH_DONE) return;
+  if (eval ? !st[inst].eval_now : (st[inst].phase != PH_LS || st[inst].eval_now)) return;
   const double step = eval ? 0.0 : st[inst].step;
   const double mu = eval ? 0.0 : st[inst].mu;
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
@@ -299,8 +303,13 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
       if (comp == 0) {
         Facc += t.val;
         if (!eval) {
-          V.ctan[k] = t.tan;
-          V.crad[k] = t.rad;
+          const double coef = (n2 > 0.0) ? (t.rad - t.tan) / n2 : 0.0;
+          double *mk = V.mk + (size_t)k * (D * (D + 1) / 2);
+          int m = 0;
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b) mk[m++] = 2.0 * wr * (((a == b) ? t.tan : 0.0) + coef * v[a] * v[b]);
         } else if (rr > 0.0) {
           const double dn = fmin(1.0, nv / rr);
           dacc += dn * dn;
@@ -328,13 +337,15 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
 
 // ---- K2: h = B^T u.  PH_CG: dz += alpha p, r -= alpha h.  PH_LS: z += step dz, dz = 0, r = -h (h is the
 // gradient of F_mu at the new point).  Evaluation ticks: partial |g|^2, g.z, |z|^2 of the true gradient only.
-__global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
+__global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                      int mode) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.cb[blockIdx.x];
   const int inst = bd.inst;
   const int phase = st[inst].phase;
-  if (phase == PH_DONE) return;
-  const bool eval = st[inst].eval_now != 0;
+  const bool eval = mode == TM_EVAL;
+  if (phase == PH_DONE || phase == PH_WAIT) return;
+  if (eval ? !st[inst].eval_now : (st[inst].eval_now != 0)) return;
   const double alpha = st[inst].alpha, step = st[inst].step;
   const int pin_end = P.zoff[inst] + P.blk;
   double gg = 0.0, gz = 0.0, zz = 0.0;
@@ -388,14 +399,15 @@ __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V
 
 // ---- ctrl_b: after the preconditioner.  PCG bookkeeping / Newton bookkeeping / termination.
 __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs V, BlockTables T, InstState *st,
-                                                       SolverCfg cfg, int *n_done) {
+                                                       SolverCfg cfg, int *n_done, int mode) {
   __shared__ double red[kSegThreads / 32];
   const int inst = blockIdx.x;
   InstState &S = st[inst];
   const int phase = S.phase;
   if (phase == PH_DONE) return;
   const int rb0 = T.rb_begin[inst], rb1 = T.rb_begin[inst + 1];
-  if (S.eval_now) {
+  if (mode == TM_EVAL) {
+    if (!S.eval_now) return;
     // certificate of the un-smoothed problem with the auxiliary variables at their
     // exact minimisers: r_link = 0, r_stat = |g_free| / (1 + |x|), p - D = g_free . z
     const int cb0 = T.cb_begin[inst], cb1 = T.cb_begin[inst + 1];
@@ -421,23 +433,31 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
     }
     return;
   }
-  double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
   if (phase == PH_CG) {
+    // one more PCG iteration done (PCG ticks, and line-search ticks for instances still inside a Newton solve)
+    double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
     if (threadIdx.x == 0) {
       rs_new += V.part_lm[inst];
       S.cg_it += 1;
       S.total_cg += 1;
       if (S.end_cg || !(rs_new > S.eta * S.eta * S.rs0) || S.cg_it >= cfg.max_cg) {
-        S.phase = PH_LS;
-        S.skip_ls = 0;
-        S.end_cg = 0;
+        S.phase = PH_WAIT;  // Newton system solved to its forcing tolerance: idle until the next line-search tick
       } else {
         S.beta = rs_new / S.rs;
         S.rs = rs_new;
       }
     }
+  }
+  if (mode == TM_CG_LAST) {  // the next tick of the batch is a line-search tick: waiting instances take it
+    if (threadIdx.x == 0 && S.phase == PH_WAIT) {
+      S.phase = PH_LS;
+      S.skip_ls = 0;
+      S.end_cg = 0;
+    }
     return;
   }
+  if (mode != TM_LS || phase != PH_LS) return;
+  double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
   // PH_LS: a new point (or the initial point) has just been evaluated with barrier parameter S.mu
   const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
   if (threadIdx.x != 0) return;

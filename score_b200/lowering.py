@@ -310,6 +310,42 @@ def lower_manhattan_arrays(arr: dict, relaxation: str = QCQP_RELAXATION, with_na
     )
 
 
+def lower_grid3d_arrays(arr: dict, relaxation: str = QCQP_RELAXATION, with_names: bool = False) -> LoweredProblem:
+    """Lower the array form produced by ``generators.grid_3d_arrays`` (config 5: 100k poses, 1M ranges)
+    without materialising Python factor objects."""
+    check_valid_relaxation(relaxation)
+    d = 3
+    R, S = arr["n_robots"], arr["n_steps"]
+    P, L = R * S, len(arr["landmarks"])
+    E = R * (S - 1)
+    base = (np.arange(R)[:, None] * S + np.arange(S - 1)[None, :]).ravel().astype(np.int32)
+    link_edge = -np.ones(P, np.int32)
+    link_edge[base + 1] = np.arange(E, dtype=np.int32)
+    K = len(arr["rng_a"])
+    i32 = lambda *v: np.asarray(v, np.int32)
+    from .generators import _chain_prefix
+
+    if with_names:
+        pose_names = [f"{_chain_prefix(r)}{t}" for r in range(R) for t in range(S)]
+        lm_names = [f"L{q}" for q in range(L)]
+        all_names = pose_names + lm_names
+        range_keys = [(all_names[a], all_names[b]) for a, b in zip(arr["rng_a"], arr["rng_b"])]
+    else:
+        pose_names, lm_names, range_keys = [], [], []
+    return LoweredProblem(
+        dim=d, relaxation=relaxation, n_instances=1,
+        pose_off=i32(0, P), lm_off=i32(0, L), edge_off=i32(0, E), rng_off=i32(0, K), prior_off=i32(0, 0),
+        seg_ptr=(np.arange(R + 1) * S).astype(np.int32), seg_inst=np.zeros(R, np.int32), link_edge=link_edge,
+        edge_i=base, edge_j=base + 1,
+        edge_t=np.ascontiguousarray(arr["odom_t"].reshape(E, 3)), edge_R=np.ascontiguousarray(arr["odom_R"].reshape(E, 3, 3)),
+        edge_k=np.full(E, arr["k_t"]), edge_tau=np.full(E, arr["k_r"]),
+        rng_a=arr["rng_a"].astype(np.int32), rng_b=arr["rng_b"].astype(np.int32),
+        rng_dist=np.asarray(arr["rng_dist"], np.float64), rng_w=np.full(K, 1.0 / arr["sigma_range"] ** 2),
+        prior_l=np.zeros(0, np.int32), prior_t=np.zeros((0, d)), prior_w=np.zeros(0),
+        pose_names=[pose_names], landmark_names=[lm_names], range_keys=[range_keys],
+    )
+
+
 def concat(problems: Sequence[LoweredProblem]) -> LoweredProblem:
     """Concatenate independent instances into one batch (block-diagonal problem)."""
     if not problems:

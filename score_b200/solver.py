@@ -27,9 +27,12 @@ class SolveStats:
     cols: int
     algorithmic_bytes: float
     instances: np.ndarray  # structured array, one record per instance
-    kernel_ms: Optional[np.ndarray] = None  # profile mode: per-kernel event time summed over profiled ticks
-    profiled_ticks: int = 0
-    kernel_bytes: Optional[np.ndarray] = None  # algorithmic bytes of one launch of each tick kernel
+    kernel_ms: Optional[np.ndarray] = None  # profile mode: per-kernel event time summed over the profiled cycles
+    profiled_cycles: int = 0
+    kernel_bytes: Optional[np.ndarray] = None  # algorithmic bytes of one launch of each tick kernel, all instances active
+    kernel_count: Optional[np.ndarray] = None  # profile mode: launches of each tick kernel in the profiled cycles
+    kernel_bytes_total: Optional[np.ndarray] = None  # algorithmic bytes of each tick kernel over the whole solve
+    cycles: int = 0
 
 
 KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_coarse_build", "k_colpass", "k_precond_rev",
@@ -120,10 +123,13 @@ class ScoreSolver:
         max_cg: int = 0,
         max_ticks: int = 0,
         cg_forcing: float = 0.0,
-        ticks_per_launch: int = 0,
+        cg_per_cycle: int = 0,
         stream: int = 0,
-        profile_ticks: int = 0,
+        profile_cycles: int = 0,
         profile_skip: int = 0,
+        cg_grow_after: int = 0,
+        cg_grow_every: int = 0,
+        coarse_every: int = 0,
         mu0: float = 0.0,
         mu_factor: float = 0.0,
         center_tol: float = 0.0,
@@ -133,9 +139,11 @@ class ScoreSolver:
         prm.device = self.device
         prm.max_newton, prm.max_cg, prm.max_ticks = max_newton, max_cg, max_ticks
         prm.kkt_tol, prm.cg_forcing = kkt_tol, cg_forcing
-        prm.ticks_per_launch = ticks_per_launch
+        prm.cg_per_cycle = cg_per_cycle
+        prm.cg_grow_after, prm.cg_grow_every = cg_grow_after, cg_grow_every
+        prm.coarse_every = coarse_every
         prm.stream = C.c_void_p(stream) if stream else None
-        prm.profile_ticks, prm.profile_skip = profile_ticks, profile_skip
+        prm.profile_cycles, prm.profile_skip = profile_cycles, profile_skip
         prm.mu0, prm.mu_factor, prm.center_tol, prm.mu_min = mu0, mu_factor, center_tol, mu_min
         st = _lib.ScoreStats()
         inst = np.zeros(self.prob.n_instances, dtype=_INST_DTYPE)
@@ -144,8 +152,10 @@ class ScoreSolver:
         self.last_stats = SolveStats(
             st.n_instances, st.n_solved, st.ticks, st.kernel_launches, st.assemble_ms, st.setup_ms, st.solve_ms,
             st.extract_ms, st.total_ms, st.nnz_reduced, st.rows, st.cols, st.algorithmic_bytes, inst,
-            kernel_ms=np.array(st.kernel_ms[:len(KERNEL_NAMES)]), profiled_ticks=int(st.profiled_ticks),
+            kernel_ms=np.array(st.kernel_ms[:len(KERNEL_NAMES)]), profiled_cycles=int(st.profiled_cycles),
             kernel_bytes=np.array(st.kernel_bytes[:len(KERNEL_NAMES)]),
+            kernel_count=np.array(st.kernel_count[:len(KERNEL_NAMES)]),
+            kernel_bytes_total=np.array(st.kernel_bytes_total[:len(KERNEL_NAMES)]), cycles=int(st.cycles),
         )
         return self.last_stats
 
@@ -161,6 +171,15 @@ class ScoreSolver:
                                             lms.ctypes.data if p.L else None, dist.ctypes.data if p.K else None))
         self.d2h_bytes = poses.nbytes + rounded.nbytes + lms.nbytes + dist.nbytes
         return poses, rounded, lms, dist
+
+    def internal(self, which: int, inst: int = 0) -> np.ndarray:
+        """Solver internals of one instance (score_get_internal): flat float64 array."""
+        n = C.c_int64()
+        _check(self._lib.score_get_internal(self._h, which, inst, None, 0, C.byref(n)))
+        out = np.empty(n.value)
+        _check(self._lib.score_get_internal(self._h, which, inst, out.ctypes.data if n.value else None, n.value,
+                                            C.byref(n)))
+        return out
 
     def sizes(self) -> Tuple[int, int, int]:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -35,13 +35,14 @@ with ScoreSolver(prob) as s:
         sys.exit(0)
     st = s.solve(**kw)  # warm
     st = s.solve(**kw)
-    stp = s.solve(profile_ticks=int(st.ticks), profile_skip=0, **kw)
+    stp = s.solve(profile_cycles=int(st.cycles), profile_skip=0, **kw)
 I = st.instances
 tot = I["cg_iters"] + I["newton_iters"]
 rep = {
     "n": n,
     "solved": int(st.n_solved),
     "ticks": int(st.ticks),
+    "cycles": int(st.cycles),
     "solve_ms": st.solve_ms,
     "assemble_ms": st.assemble_ms,
     "setup_ms": st.setup_ms,
@@ -55,6 +56,9 @@ rep = {
     "profiled_solve_ms": stp.solve_ms,
     "kernel_ms_total": {k: float(v) for k, v in zip(KERNEL_NAMES, stp.kernel_ms)},
     "kernel_share": {k: float(v / stp.kernel_ms.sum()) for k, v in zip(KERNEL_NAMES, stp.kernel_ms)},
+    "kernel_launches": {k: int(v) for k, v in zip(KERNEL_NAMES, stp.kernel_count)},
+    "kernel_gbs_whole_solve": {k: (float(b / (v * 1e6)) if v > 0 else None)
+                               for k, v, b in zip(KERNEL_NAMES, stp.kernel_ms, stp.kernel_bytes_total)},
 }
 print(json.dumps(rep, indent=1))
 with open(out, "w") as f:

@@ -202,3 +202,103 @@ def test_batch_matches_single_bitwise(built_lib, golden):
         s3.solve()
         p3, _, _, _ = s3.solution()
     assert np.array_equal(p3, poses[a.P + b.P : a.P + b.P + c.P])
+
+
+@pytest.mark.parametrize("name", ["man4", "mc0", "mc0_small", "grid3d"])
+def test_coarse_inverse_matches_dense_reference(built_lib, golden, name):
+    """The on-chip coarse level (sorted-list accumulation + register-tiled Gauss-Jordan, coarse.cuh) against a
+    dense numpy build of A_c = Z^T H_range Z from the same per-range curvature blocks and frames."""
+    from score_b200 import _lib, generators
+    from score_b200.lowering import lower_factor_graph
+
+    if name == "grid3d":
+        fg = generators.grid_3d_factor_graph(
+            generators.grid_3d_arrays(7, n_robots=4, n_steps=30, grid=8, n_landmarks=5, n_ranges=300))
+    else:
+        fg, _ = golden(name)
+    p = lower_factor_graph(fg)
+    d, d1 = p.dim, p.dim + 1
+    blk, nm = d * d1, d * (d + 1) // 2
+    from score_b200.solver import ScoreSolver
+
+    with ScoreSolver(p) as s:
+        st = s.solve()
+        Ainv = s.internal(_lib.SCORE_INT_COARSE_INV)
+        mk = s.internal(_lib.SCORE_INT_RANGE_CURV).reshape(p.K, nm)
+        G = s.internal(_lib.SCORE_INT_FRAMES).reshape(p.P, d, d1)
+    assert st.n_solved == 1
+    nsegfree, nb = p.n_seg - 1, (p.n_seg - 1) * blk
+    nc = nb + p.L * d
+    assert Ainv.size == nc * nc
+    Ainv = Ainv.reshape(nc, nc)
+    seg_of_pose = np.searchsorted(p.seg_ptr, np.arange(p.P), side="right") - 1
+
+    def jac(owner):  # d x nc map from coarse coordinates to the translation of an endpoint
+        J = np.zeros((d, nc))
+        if owner >= p.P:
+            q = owner - p.P
+            J[:, nb + q * d : nb + (q + 1) * d] = np.eye(d)
+        else:
+            slot = seg_of_pose[owner] - 1
+            if slot >= 0:
+                h = np.append(G[owner][:, d], 1.0)
+                for r in range(d):
+                    J[r, slot * blk + r * d1 : slot * blk + (r + 1) * d1] = h
+        return J
+
+    A = np.zeros((nc, nc))
+    iu = np.triu_indices(d)
+    for k in range(p.K):
+        M = np.zeros((d, d))
+        M[iu] = mk[k]
+        M = M + M.T - np.diag(np.diag(M))
+        Ja, Jb = jac(int(p.rng_a[k])), jac(int(p.rng_b[k]))
+        Z = Ja - Jb
+        A += Z.T @ M @ Z
+        # regularisation 1e-6 * 2 w on the diagonal blocks (one term per incidence; a - b when both share a slot)
+        w2r = 1e-6 * 2.0 * p.rng_w[k]
+        sa = seg_of_pose[p.rng_a[k]] - 1 if p.rng_a[k] < p.P else nsegfree + p.rng_a[k] - p.P
+        sb = seg_of_pose[p.rng_b[k]] - 1 if p.rng_b[k] < p.P else nsegfree + p.rng_b[k] - p.P
+        if sa == sb:
+            A += w2r * Z.T @ Z
+        else:
+            A += w2r * (Ja.T @ Ja + Jb.T @ Jb)
+    for q, wq in zip(p.prior_l, p.prior_w):
+        A[nb + q * d + np.arange(d), nb + q * d + np.arange(d)] += 2.0 * wq
+    for i in range(nc):
+        if not A[i, i] > 0:
+            A[i, i] = 1.0
+    ref = np.linalg.inv(A)
+    assert np.array_equal(Ainv, Ainv.T)
+    assert np.abs(Ainv - ref).max() <= 1e-8 * np.abs(ref).max() * max(1.0, np.linalg.cond(A) * 1e-8)
+    assert np.abs(Ainv @ A - np.eye(nc)).max() <= 1e-6
+
+
+@pytest.mark.parametrize("relax", ["QCQP", "SOCP"])
+def test_solution_parity_3d(built_lib, relax):
+    """d = 3 (SURVEY 8(d) config 5 at test size): assembly bit-exact, solution certified by the oracle, objective
+    equal to the oracle's own barrier solve, SO(3) rounding equal to the SVD rule."""
+    from oracle import score_oracle as so
+    from score_b200 import _lib, generators
+
+    fg = generators.grid_3d_factor_graph(
+        generators.grid_3d_arrays(11, n_robots=3, n_steps=40, grid=8, n_landmarks=5, n_ranges=260))
+    prob = so.assemble(fg, relax)
+    with _solver(fg, relax) as s:
+        indptr, indices, values, w, b, shape = s.csr(_lib.SCORE_CSR_FULL, 0)
+        st = s.solve()
+        poses, rounded, lms, dist = s.solution()
+    assert shape == prob.B.shape
+    assert np.array_equal(indptr, prob.B.indptr) and np.array_equal(indices, prob.B.indices)
+    assert np.array_equal(values, prob.B.data) and np.array_equal(w, prob.w) and np.array_equal(b, prob.b)
+    rec = st.instances[0]
+    assert rec["solved"] == 1
+    pq, xq, _ = so.solve(fg, so.QCQP)
+    f_star = so.objective(pq, xq)
+    assert abs(rec["objective"] - f_star) <= 1e-4 * max(1.0, abs(f_star))
+    x = _full_x(prob, poses, lms, dist)
+    assert abs(so.objective(prob, x) - rec["objective"]) <= 1e-9 * max(1.0, abs(f_star))
+    if relax == "QCQP":
+        assert so.kkt_qcqp(prob, x)["rel_kkt"] <= 1e-6
+    assert np.abs(rounded - so.round_rotations(poses)).max() < 1e-8
+    assert np.abs(np.linalg.det(rounded) - 1).max() < 1e-12
