@@ -16,8 +16,8 @@
 //   * incidences sorted by slot      -> diagonal blocks, one warp per slot run;
 //   * ranges sorted by slot pair     -> upper off-diagonal blocks, contiguous runs per warp;
 // so every block has exactly one owning warp, the summation order is fixed and no atomics are needed.
-// The nc x nc matrix is then inverted by Gauss-Jordan elimination with the matrix held in registers
-// (TS x TS tile per thread; one pivot row / column broadcast through shared memory per step).
+// The nc x nc matrix is then inverted by symmetric sweeps (Gauss-Jordan in its symmetry-preserving form) with
+// the matrix held in registers (TS x TS tile per thread; one pivot row broadcast through shared memory per step).
 #pragma once
 #include "common.cuh"
 
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
   using CD = CoarseDims<D>;
   constexpr int D1 = CD::D1, BLK = CD::BLK, NM = CD::NM, NH = CD::NH, SB = CD::SB;
   constexpr int NP = 32 * TS;  // padded matrix dimension
+  constexpr int NS = NP + 1;   // shared-memory row stride (odd: transposed reads are bank-conflict free)
   constexpr int NW = kCoarseThreads / 32;
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
@@ -132,13 +133,12 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
     if (threadIdx.x == 0) st[inst].c_age += 1;
     return;
   }
-  double *A = sm;                       // NP x NP
-  double *rowb = A + NP * NP;           // 2 x NP
-  double *colb = rowb + 2 * NP;         // 2 x NP
-  double *pivb = colb + 2 * NP;         // 2 (+2 pad)
-  double *stage = pivb + 4;             // NW x STAGE
+  double *A = sm;                       // NP x NS
+  double *rowb = A + NP * NS;           // 2 x NP (NP * NS is even: 16-byte aligned)
+  double *pivb = rowb + 2 * NP;         // 2
+  double *stage = pivb + 2;             // NW x STAGE
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i < NP * NP; i += kCoarseThreads) A[i] = 0.0;
+  for (int i = tid; i < NP * NS; i += kCoarseThreads) A[i] = 0.0;
   __syncthreads();
   const int nb = P.c_nb[inst], nsegfree = nb / BLK;
   const int k0 = P.rng_off[inst];
@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
         const int i2 = coarse_index<D>(slot, nsegfree, nb, r, cc), i3 = coarse_index<D>(slot, nsegfree, nb, rr, c);
         const double v = acc[a];
         if (i0 >= 0 && i1 >= 0) {
-          A[i0 * NP + i1] += v;
-          if (i1 != i0) A[i1 * NP + i0] += v;
+          A[i0 * NS + i1] += v;
+          if (i1 != i0) A[i1 * NS + i0] += v;
         }
         if (c != cc && r != rr && i2 >= 0 && i3 >= 0) {  // (r, c') x (r', c): distinct image only when both differ
-          A[i2 * NP + i3] += v;
-          A[i3 * NP + i2] += v;
+          A[i2 * NS + i3] += v;
+          A[i3 * NS + i2] += v;
         }
       }
     }
@@ -258,10 +258,10 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
         const int c = pc[a], cc = pcc[a];
         const double v = -acc[a];
         const int i0 = coarse_index<D>(lo, nsegfree, nb, r, c), i1 = coarse_index<D>(hi, nsegfree, nb, rr, cc);
-        if (i0 >= 0 && i1 >= 0) A[i0 * NP + i1] += v;
+        if (i0 >= 0 && i1 >= 0) A[i0 * NS + i1] += v;
         if (r != rr) {
           const int i2 = coarse_index<D>(lo, nsegfree, nb, rr, c), i3 = coarse_index<D>(hi, nsegfree, nb, r, cc);
-          if (i2 >= 0 && i3 >= 0) A[i2 * NP + i3] += v;
+          if (i2 >= 0 && i3 >= 0) A[i2 * NS + i3] += v;
         }
       }
     }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
   if (tid == 0) {
     for (int pl = P.prior_off[inst]; pl < P.prior_off[inst + 1]; ++pl) {
       const int q = P.prior_l[pl];
-      for (int r = 0; r < D; ++r) A[(nb + q * D + r) * NP + nb + q * D + r] += 2.0 * P.prior_w[pl];
+      for (int r = 0; r < D; ++r) A[(nb + q * D + r) * NS + nb + q * D + r] += 2.0 * P.prior_w[pl];
     }
   }
   __syncthreads();
@@ -283,33 +283,34 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
 #pragma unroll
     for (int c = 0; c < TS; ++c) {
       const int i = ty * TS + r, j = tx * TS + c;
-      double v = (i <= j) ? A[i * NP + j] : A[j * NP + i];
+      double v = (i <= j) ? A[i * NS + j] : A[j * NS + i];
       if (i == j && (i >= n || !(v > 0.0))) v = 1.0;  // padding / coordinate without curvature: identity
       Tl[r][c] = v;
     }
-  // ---- in-place Gauss-Jordan inverse (SPD, no pivoting)
+  // ---- symmetric sweep of every pivot (SPD, no pivoting):  a_kk <- -1/p, a_ik <- a_ik/p, a_kj <- a_kj/p,
+  // a_ij <- a_ij - a_ik a_kj / p.  The matrix stays symmetric, so only the pivot ROW is broadcast (its owner is
+  // one warp) and the column factors are read from the same buffer.  Publishing p - 1 in place of p makes the
+  // generic rank-1 update produce the pivot row and column too; only a_kk itself is patched.  Result: -A^-1.
   for (int k = 0; k < n; ++k) {
     const int kt = k / TS, kl = k - kt * TS, buf = (k & 1) * NP;
-    if (ty == kt) {
+    if (ty == kt) {  // warp-uniform
+      double rowv[TS];
 #pragma unroll
       for (int r = 0; r < TS; ++r)
         if (r == kl) {
 #pragma unroll
-          for (int c = 0; c < TS; ++c) rowb[buf + tx * TS + c] = Tl[r][c];
+          for (int c = 0; c < TS; ++c) rowv[c] = Tl[r][c];
         }
-    }
-    if (tx == kt) {
+      if (tx == kt) {
 #pragma unroll
-      for (int c = 0; c < TS; ++c)
-        if (c == kl) {
-#pragma unroll
-          for (int r = 0; r < TS; ++r) colb[buf + ty * TS + r] = Tl[r][c];
-          if (ty == kt) {
-#pragma unroll
-            for (int r = 0; r < TS; ++r)
-              if (r == kl) pivb[k & 1] = 1.0 / Tl[r][c];
+        for (int c = 0; c < TS; ++c)
+          if (c == kl) {
+            pivb[k & 1] = 1.0 / rowv[c];
+            rowv[c] -= 1.0;
           }
-        }
+      }
+#pragma unroll
+      for (int c = 0; c < TS; ++c) rowb[buf + tx * TS + c] = rowv[c];
     }
     __syncthreads();
     const double inv = pivb[k & 1];
@@ -317,43 +318,29 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
 #pragma unroll
     for (int c = 0; c < TS; ++c) rc[c] = rowb[buf + tx * TS + c] * inv;
 #pragma unroll
-    for (int r = 0; r < TS; ++r) cr[r] = colb[buf + ty * TS + r];
+    for (int r = 0; r < TS; ++r) cr[r] = rowb[buf + ty * TS + r];
 #pragma unroll
     for (int r = 0; r < TS; ++r)
 #pragma unroll
       for (int c = 0; c < TS; ++c) Tl[r][c] -= cr[r] * rc[c];
-    if (ty == kt) {  // pivot row: a_kj / p
+    if (ty == kt && tx == kt) {
 #pragma unroll
       for (int r = 0; r < TS; ++r)
-        if (r == kl) {
 #pragma unroll
-          for (int c = 0; c < TS; ++c) Tl[r][c] = rc[c];
-        }
-    }
-    if (tx == kt) {  // pivot column: -a_ik / p ;  pivot: 1 / p
-#pragma unroll
-      for (int c = 0; c < TS; ++c)
-        if (c == kl) {
-#pragma unroll
-          for (int r = 0; r < TS; ++r) Tl[r][c] = -cr[r] * inv;
-          if (ty == kt) {
-#pragma unroll
-            for (int r = 0; r < TS; ++r)
-              if (r == kl) Tl[r][c] = inv;
-          }
-        }
+        for (int c = 0; c < TS; ++c)
+          if (r == kl && c == kl) Tl[r][c] = -inv;
     }
   }
-  // ---- write back, symmetrise, store
+  // ---- write back (negated), symmetrise, store
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < TS; ++r)
 #pragma unroll
-    for (int c = 0; c < TS; ++c) A[(ty * TS + r) * NP + tx * TS + c] = Tl[r][c];
+    for (int c = 0; c < TS; ++c) A[(ty * TS + r) * NS + tx * TS + c] = -Tl[r][c];
   __syncthreads();
   double *out = P.c_Ainv + P.c_moff[inst];
   for (int i = wid; i < n; i += NW)
-    for (int j = lane; j < n; j += 32) out[i * n + j] = 0.5 * (A[i * NP + j] + A[j * NP + i]);  // exactly symmetric
+    for (int j = lane; j < n; j += 32) out[i * n + j] = 0.5 * (A[i * NS + j] + A[j * NS + i]);  // exactly symmetric
   if (tid == 0) {
     st[inst].mu_c = st[inst].mu;
     st[inst].c_age = 1;
@@ -363,7 +350,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
 template <int D>
 inline size_t coarse_smem_bytes_d(int ts) {
   const size_t np = 32 * (size_t)ts;
-  return sizeof(double) * (np * np + 4 * np + 4 + (size_t)(kCoarseThreads / 32) * CoarseDims<D>::STAGE);
+  return sizeof(double) * (np * (np + 1) + 2 * np + 2 + (size_t)(kCoarseThreads / 32) * CoarseDims<D>::STAGE);
 }
 inline size_t coarse_smem_bytes(int d, int ts) { return d == 2 ? coarse_smem_bytes_d<2>(ts) : coarse_smem_bytes_d<3>(ts); }
 inline int coarse_tile_size(int nmax) { return (nmax + 31) / 32; }

@@ -84,6 +84,19 @@ __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, do
   return t;
 }
 
+// Value only (line search): phi_mu(n).
+__device__ __forceinline__ double range_value(double n, double r, double w, double mu) {
+  if (!(r > 0.0)) return w * n * n;
+  if (mu == 0.0) {
+    const double e = fmax(n - r, 0.0);
+    return w * e * e;
+  }
+  const double q = n / r, kap = mu / (w * r * r);
+  const double e = barrier_eps(q, kap);
+  const double gap = r * (q - 1.0 + e);
+  return w * gap * gap - mu * log(e * (2.0 - e));
+}
+
 // res = B z - b   (initialisation only)
 __global__ void __launch_bounds__(kThreads) k_residual(DevProblem P, const double *__restrict__ z, double *res) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,34 +172,39 @@ __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVec
   double sums[kLsSums];
 #pragma unroll
   for (int i = 0; i < kLsSums; ++i) sums[i] = 0.0;
-  const int nrows = bd.i1 - bd.i0;
-  for (int li = threadIdx.x; li < nrows; li += kThreads) {
-    const int row = bd.i0 + li;
-    if (row >= rr0 && row < rr1) {
-      const int rel = row - rr0;
-      if (rel % D != 0) continue;
-      const int k = P.rng_off[inst] + rel / D;
+  // plain (quadratic) rows of this block: relative-pose rows before the ranges, prior rows after them
+  auto plain = [&](int r0, int r1) {
+    for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
+      const double v = V.res[row], q = V.bdz[row], wr = P.w[row];
+      sums[0] += wr * v * v;
+      sums[1] += wr * v * q;
+      sums[2] += wr * q * q;
+    }
+  };
+  plain(bd.i0, min(bd.i1, rr0));
+  plain(max(bd.i0, rr1), bd.i1);
+  // range terms: one thread per range (a block never splits a range: kRowsPerBlock is a multiple of D)
+  const int ra = max(bd.i0, rr0), rb = min(bd.i1, rr1);
+  if (rb > ra) {
+    const int nrng = (rb - ra) / D, kfirst = P.rng_off[inst] + (ra - rr0) / D;
+    for (int q = threadIdx.x; q < nrng; q += kThreads) {
+      const int row = ra + q * D, k = kfirst + q;
       const double rr = P.rng_dist[k], wk = P.rng_w[k];
       double A = 0.0, Bq = 0.0, C = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        const double v = V.res[row + c], q = V.bdz[row + c];
+        const double v = V.res[row + c], qq = V.bdz[row + c];
         A += v * v;
-        Bq += v * q;
-        C += q * q;
+        Bq += v * qq;
+        C += qq * qq;
       }
 #pragma unroll
       for (int c = 0; c < kNumCand; ++c) {
         const double a = ls_candidate(c);
         const double n = sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C)));
-        sums[3 + c] += range_term(n, rr, wk, mu, true).val;
+        sums[3 + c] += range_value(n, rr, wk, mu);
       }
-      sums[3 + kNumCand] += range_term(sqrt(A), rr, wk, mu, true).val;
-    } else {
-      const double v = V.res[row], q = V.bdz[row], wr = P.w[row];
-      sums[0] += wr * v * v;
-      sums[1] += wr * v * q;
-      sums[2] += wr * q * q;
+      sums[3 + kNumCand] += range_value(sqrt(A), rr, wk, mu);
     }
   }
 #pragma unroll
@@ -277,55 +295,52 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
   const double mu = eval ? 0.0 : st[inst].mu;
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
-  const int nrows = bd.i1 - bd.i0;
   double Facc = 0.0, dacc = 0.0;
-  // two sweeps so that every thread of a range reads the un-updated residual of its siblings
-  double newv[(kRowsPerBlock + kThreads - 1) / kThreads];
-  int j = 0;
-  for (int li = threadIdx.x; li < nrows; li += kThreads, ++j) {
-    const int row = bd.i0 + li;
-    const double wr = P.w[row];
-    double out;
-    if (row >= rr0 && row < rr1) {
-      const int rel = row - rr0, comp = rel % D, base = row - comp;
-      const int k = P.rng_off[inst] + rel / D;
-      const double rr = P.rng_dist[k];
+  auto plain = [&](int r0, int r1) {
+    for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
+      const double wr = P.w[row];
+      const double v = V.res[row] + step * V.bdz[row];
+      if (!eval) V.res[row] = v;
+      Facc += wr * v * v;
+      V.u[row] = 2.0 * wr * v;
+    }
+  };
+  plain(bd.i0, min(bd.i1, rr0));
+  plain(max(bd.i0, rr1), bd.i1);
+  // range terms: one thread per range
+  const int ra = max(bd.i0, rr0), rb = min(bd.i1, rr1);
+  if (rb > ra) {
+    const int nrng = (rb - ra) / D, kfirst = P.rng_off[inst] + (ra - rr0) / D;
+    for (int q = threadIdx.x; q < nrng; q += kThreads) {
+      const int row = ra + q * D, k = kfirst + q;
+      const double rr = P.rng_dist[k], wr = P.rng_w[k];
       double v[D], n2 = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        v[c] = V.res[base + c] + step * V.bdz[base + c];
+        v[c] = V.res[row + c] + step * V.bdz[row + c];
         n2 += v[c] * v[c];
       }
-      newv[j] = v[comp];
       const double nv = sqrt(n2);
-      const RangeTerm t = range_term(nv, rr, wr, mu, comp == 0);
-      out = t.tan * v[comp];
-      if (comp == 0) {
-        Facc += t.val;
-        if (!eval) {
-          const double coef = (n2 > 0.0) ? (t.rad - t.tan) / n2 : 0.0;
-          double *mk = V.mk + (size_t)k * (D * (D + 1) / 2);
-          int m = 0;
+      const RangeTerm t = range_term(nv, rr, wr, mu, true);
+      Facc += t.val;
 #pragma unroll
-          for (int a = 0; a < D; ++a)
-#pragma unroll
-            for (int b = a; b < D; ++b) mk[m++] = 2.0 * wr * (((a == b) ? t.tan : 0.0) + coef * v[a] * v[b]);
-        } else if (rr > 0.0) {
-          const double dn = fmin(1.0, nv / rr);
-          dacc += dn * dn;
-        }
+      for (int c = 0; c < D; ++c) {
+        if (!eval) V.res[row + c] = v[c];
+        V.u[row + c] = 2.0 * wr * t.tan * v[c];
       }
-    } else {
-      newv[j] = V.res[row] + step * V.bdz[row];
-      out = newv[j];
-      Facc += wr * out * out;
+      if (!eval) {
+        const double coef = (n2 > 0.0) ? (t.rad - t.tan) / n2 : 0.0;
+        double *mk = V.mk + (size_t)k * (D * (D + 1) / 2);
+        int m = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+          for (int b = a; b < D; ++b) mk[m++] = 2.0 * wr * (((a == b) ? t.tan : 0.0) + coef * v[a] * v[b]);
+      } else if (rr > 0.0) {
+        const double dn = fmin(1.0, nv / rr);
+        dacc += dn * dn;
+      }
     }
-    V.u[row] = 2.0 * wr * out;
-  }
-  __syncthreads();
-  if (!eval) {
-    j = 0;
-    for (int li = threadIdx.x; li < nrows; li += kThreads, ++j) V.res[bd.i0 + li] = newv[j];
   }
   const double Ftot = block_sum<kThreads>(Facc, red);
   const double dtot = block_sum<kThreads>(dacc, red);
