@@ -643,7 +643,7 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   if (pf) pf->mark(KI_LINESEARCH);
   k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
+  k_ctrl_a<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, P.n_inst);
   if (pf) pf->mark(KI_ROWUPDATE);
   k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
   n += 4;
@@ -656,7 +656,7 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
   n += 1 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS);
+  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS);
   if (pf) pf->mark(KI_PUPDATE);
   k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
   if (pf) pf->mark(-1);
@@ -672,7 +672,7 @@ static int launch_eval_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t 
   if (pf) pf->mark(KI_COLPASS);
   k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL);
+  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL);
   if (pf) pf->mark(-1);
   return 3;
 }
@@ -685,12 +685,12 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   if (pf) pf->mark(KI_ROWPASS);
   k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<P.n_inst, kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg);
+  k_ctrl_a<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, P.n_inst);
   if (pf) pf->mark(KI_COLPASS);
   k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_CG);
   n += 3 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG);
+  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG);
   if (pf) pf->mark(KI_PUPDATE);
   k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
   if (pf) pf->mark(-1);
@@ -825,7 +825,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     *out = exec;
     return SCORE_OK;
   };
-  const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 3;
+  const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 4;
   const int grow_after = prm.cg_grow_after > 0 ? prm.cg_grow_after : (1 << 30);
   const int grow_every = prm.cg_grow_every > 0 ? prm.cg_grow_every : 8;
   const int kernels_per_cg_tick = 7 + (h->c_nmax > 0 ? 1 : 0), kernels_per_ls_tick = 10 + (h->c_nmax > 0 ? 2 : 0) + 3;

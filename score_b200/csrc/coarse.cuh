@@ -372,21 +372,18 @@ __global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < n; i += kCoarseApplyThreads) cs[i] = c[i];
   __syncthreads();
-  // two rows per warp step: all loads of both rows are issued before the reductions
-  for (int i = 2 * wid; i < n; i += 2 * NW) {
-    const bool two = i + 1 < n;
-    double a0 = 0.0, a1 = 0.0;
+  // four rows per warp step: the loads of all four rows are in flight before the reductions
+  for (int i = 4 * wid; i < n; i += 4 * NW) {
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
     for (int j = lane; j < n; j += 32) {
       const double cj = cs[j];
-      a0 += __ldg(Ai + (size_t)i * n + j) * cj;
-      if (two) a1 += __ldg(Ai + (size_t)(i + 1) * n + j) * cj;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (i + t < n) a[t] += __ldg(Ai + (size_t)(i + t) * n + j) * cj;
     }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (lane == 0) {
-      ys[i] = a0;
-      if (two) ys[i + 1] = a1;
-    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) a[t] = warp_sum(a[t]);
+    if (lane < 4 && i + lane < n) ys[i + lane] = a[lane & 3];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += kCoarseApplyThreads) y[i] = ys[i];

@@ -118,12 +118,35 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
   if (phase == PH_LS && st[bd.inst].skip_ls) return;  // start point: no direction yet (bdz stays 0)
   const double *__restrict__ x = (phase == PH_CG) ? V.p : V.dz;
   const int nrows = bd.i1 - bd.i0;
-  for (int li = threadIdx.x; li < nrows; li += kThreads) {
-    const int row = bd.i0 + li;
-    const int k0 = P.indptr[row], k1 = P.indptr[row + 1];
-    double acc = 0.0;
-    for (int k = k0; k < k1; ++k) acc += P.vals[k] * __ldg(x + P.cols[k]);
-    sq[li] = acc;
+  {
+    // rows li = tid + t * kThreads, t < 3 (kRowsPerBlock = 3 kThreads): the index loads of all three rows are
+    // issued before the value / gather loads so that each thread keeps several requests in flight
+    constexpr int RPT = kRowsPerBlock / kThreads;
+    int k0[RPT], k1[RPT];
+#pragma unroll
+    for (int t = 0; t < RPT; ++t) {
+      const int li = threadIdx.x + t * kThreads;
+      const bool ok = li < nrows;
+      k0[t] = ok ? P.indptr[bd.i0 + li] : 0;
+      k1[t] = ok ? P.indptr[bd.i0 + li + 1] : 0;
+    }
+    double acc[RPT];
+#pragma unroll
+    for (int t = 0; t < RPT; ++t) acc[t] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {  // rows of the reduced operator hold at most d + 2 <= 5 entries
+#pragma unroll
+      for (int t = 0; t < RPT; ++t) {
+        const int k = k0[t] + j;
+        if (k < k1[t]) acc[t] += P.vals[k] * __ldg(x + P.cols[k]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < RPT; ++t) {
+      for (int k = k0[t] + 6; k < k1[t]; ++k) acc[t] += P.vals[k] * __ldg(x + P.cols[k]);  // (never taken today)
+      const int li = threadIdx.x + t * kThreads;
+      if (li < nrows) sq[li] = acc[t];
+    }
   }
   __syncthreads();
   if (phase == PH_LS) {
@@ -214,24 +237,26 @@ __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVec
   }
 }
 
-// Fixed-order sum of part[i0..i1) with stride `stride`, by a 128-thread CTA; valid in thread 0.
-__device__ __forceinline__ double ctrl_sum(const double *part, int i0, int i1, int stride, int off, double *red) {
+// Fixed-order sum of part[i0..i1) with stride `stride`, by one warp (the controllers run one warp per
+// instance); valid in every lane.
+__device__ __forceinline__ double ctrl_sum(const double *part, int i0, int i1, int stride, int off) {
   double acc = 0.0;
-  for (int i = i0 + threadIdx.x; i < i1; i += kSegThreads) acc += part[(size_t)i * stride + off];
-  return block_sum<kSegThreads>(acc, red);
+  for (int i = i0 + (threadIdx.x & 31); i < i1; i += 32) acc += part[(size_t)i * stride + off];
+  return warp_sum(acc);
 }
 
-// ---- ctrl_a: PCG step length / line-search decision / barrier update.  One CTA per instance.
-__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg) {
-  __shared__ double red[kSegThreads / 32];
-  const int inst = blockIdx.x;
+// ---- ctrl_a: PCG step length / line-search decision / barrier update.  One warp per instance.
+__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg, int n_inst) {
+  const int inst = blockIdx.x * (kSegThreads / 32) + (threadIdx.x >> 5);
+  if (inst >= n_inst) return;
+  const int lane = threadIdx.x & 31;
   InstState &S = st[inst];
   const int phase = S.phase;
   if ((phase != PH_CG && phase != PH_LS) || S.eval_now) return;
   const int b0 = T.rb_begin[inst], b1 = T.rb_begin[inst + 1];
   if (phase == PH_CG) {
-    const double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0, red);
-    if (threadIdx.x == 0) {
+    const double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0);
+    if (lane == 0) {
       if (pHp > 0.0 && pHp > 1e-30 * fabs(S.rs) && isfinite(pHp)) {
         S.alpha = S.rs / pHp;
         S.dec += S.alpha * S.rs;  // -g.dz accumulates: Newton decrement^2 of the current solve
@@ -244,15 +269,15 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
   }
   // PH_LS
   if (S.skip_ls) {
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       S.step = 0.0;
       S.mu_ls = S.mu;
     }
     return;
   }
   double tot[kLsSums];
-  for (int i = 0; i < kLsSums; ++i) tot[i] = ctrl_sum(V.part_ls, b0, b1, kLsSums, i, red);
-  if (threadIdx.x == 0) {
+  for (int i = 0; i < kLsSums; ++i) tot[i] = ctrl_sum(V.part_ls, b0, b1, kLsSums, i);
+  if (lane == 0) {
     double best = tot[0] + tot[3 + kNumCand], step = 0.0;
     for (int c = 0; c < kNumCand; ++c) {
       const double a = ls_candidate(c);
@@ -415,8 +440,9 @@ __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V
 // ---- ctrl_b: after the preconditioner.  PCG bookkeeping / Newton bookkeeping / termination.
 __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs V, BlockTables T, InstState *st,
                                                        SolverCfg cfg, int *n_done, int mode) {
-  __shared__ double red[kSegThreads / 32];
-  const int inst = blockIdx.x;
+  const int inst = blockIdx.x * (kSegThreads / 32) + (threadIdx.x >> 5);
+  if (inst >= P.n_inst) return;
+  const int lane = threadIdx.x & 31;
   InstState &S = st[inst];
   const int phase = S.phase;
   if (phase == PH_DONE) return;
@@ -426,12 +452,12 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
     // certificate of the un-smoothed problem with the auxiliary variables at their
     // exact minimisers: r_link = 0, r_stat = |g_free| / (1 + |x|), p - D = g_free . z
     const int cb0 = T.cb_begin[inst], cb1 = T.cb_begin[inst + 1];
-    const double F = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
-    const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 2, 1, red);
-    const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0, red);
-    const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1, red);
-    const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2, red);
-    if (threadIdx.x != 0) return;
+    const double F = ctrl_sum(V.part_upd, rb0, rb1, 2, 0);
+    const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 2, 1);
+    const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0);
+    const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1);
+    const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2);
+    if (lane != 0) return;
     S.F = F;
     S.gnorm = sqrt(gg);
     S.xnorm = sqrt(zz + dn2);
@@ -450,8 +476,8 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
   }
   if (phase == PH_CG) {
     // one more PCG iteration done (PCG ticks, and line-search ticks for instances still inside a Newton solve)
-    double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
-    if (threadIdx.x == 0) {
+    double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0);
+    if (lane == 0) {
       rs_new += V.part_lm[inst];
       S.cg_it += 1;
       S.total_cg += 1;
@@ -464,7 +490,7 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
     }
   }
   if (mode == TM_CG_LAST) {  // the next tick of the batch is a line-search tick: waiting instances take it
-    if (threadIdx.x == 0 && S.phase == PH_WAIT) {
+    if (lane == 0 && S.phase == PH_WAIT) {
       S.phase = PH_LS;
       S.skip_ls = 0;
       S.end_cg = 0;
@@ -472,10 +498,10 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
     return;
   }
   if (mode != TM_LS || phase != PH_LS) return;
-  double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0, red);
+  double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0);
   // PH_LS: a new point (or the initial point) has just been evaluated with barrier parameter S.mu
-  const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 2, 0, red);
-  if (threadIdx.x != 0) return;
+  const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 2, 0);
+  if (lane != 0) return;
   rs_new += V.part_lm[inst];
   S.Fmu = Fmu;
   if (!S.skip_ls) S.newton_it += 1;

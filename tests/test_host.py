@@ -287,3 +287,39 @@ def test_shim_pickle_roundtrip(golden):
     a, b = graph_to_arrays(fg), graph_to_arrays(fg2)
     for k in a:
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_grid3d_generator_and_lowering():
+    """SURVEY 8(d) config 5 at test size: unit lattice steps, exact range count, distinct keys, and the direct
+    array lowering equals lowering the FactorGraphData objects."""
+    from score_b200.lowering import lower_grid3d_arrays
+
+    kw = dict(n_robots=3, n_steps=25, grid=6, n_landmarks=4, n_ranges=120)
+    arr = generators.grid_3d_arrays(5, **kw)
+    arr2 = generators.grid_3d_arrays(5, **kw)
+    for k in arr:
+        assert np.array_equal(np.asarray(arr[k]), np.asarray(arr2[k])), k
+    assert len(arr["rng_a"]) == 120
+    assert len({(a, b) for a, b in zip(arr["rng_a"], arr["rng_b"])}) == 120
+    steps = np.linalg.norm(np.diff(arr["pos"], axis=1), axis=-1)
+    assert np.allclose(steps, 1.0) and arr["pos"].min() >= 0 and arr["pos"].max() <= 6
+    Rm = arr["rot"]
+    assert np.abs(Rm @ np.transpose(Rm, (0, 1, 3, 2)) - np.eye(3)).max() < 1e-12 and np.allclose(np.linalg.det(Rm), 1)
+    oR = arr["odom_R"]
+    assert np.abs(oR @ np.transpose(oR, (0, 1, 3, 2)) - np.eye(3)).max() < 1e-12
+    # inter-robot ranges connect poses of the same timestep
+    rr = arr["rng_b"] < 75
+    assert np.array_equal(arr["rng_a"][rr] % 25, arr["rng_b"][rr] % 25)
+    fg = generators.grid_3d_factor_graph(arr)
+    assert fg.dimension == 3 and len(fg.unconnected_variable_names) == 0
+    a, b = lower_grid3d_arrays(arr, with_names=True), lower_factor_graph(fg)
+    for f in ("pose_off", "lm_off", "edge_off", "rng_off", "seg_ptr", "link_edge", "edge_i", "edge_j", "rng_a", "rng_b",
+              "edge_t", "edge_R", "edge_k", "edge_tau", "rng_dist", "rng_w"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.range_keys == b.range_keys
+    B, w, _ = csr_from_lowered(a)
+    prob = so.assemble(fg, so.QCQP)
+    assert np.array_equal(B.indptr, prob.B.indptr) and np.array_equal(B.indices, prob.B.indices)
+    assert np.array_equal(B.data, prob.B.data) and np.array_equal(w, prob.w)
+    with pytest.raises(ValueError):
+        generators.grid_3d_arrays(5, n_robots=2, n_steps=3, grid=4, n_landmarks=1, n_ranges=10**6)
