@@ -9,11 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscore_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "assemble.cuh", "precond.cuh", "solver.cuh", "extract.cuh", "../../include/score_b200.h"]
+HEADERS = ["common.cuh", "assemble.cuh", "precond.cuh", "coarse.cuh", "solver.cuh", "extract.cuh", "../../include/score_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 
 

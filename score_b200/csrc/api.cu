@@ -1,9 +1,12 @@
 // libscore_b200 — C ABI (include/score_b200.h) over the sm_100a kernels.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "assemble.cuh"
@@ -22,6 +25,9 @@ struct ScoreHandle_ {
   DevProblem P{};
   SolverVecs V{};
   BlockTables T{};
+  WorkLists W{};
+  int *wl_mem = nullptr;  // backing store of the work lists
+  int n_sm = 148;
   InstState *st = nullptr;
   int *d_ndone = nullptr;
   int *h_ndone = nullptr;  // pinned, two slots (double-buffered completion count)
@@ -57,7 +63,8 @@ template <typename T>
 int dalloc(ScoreHandle_ *h, T **ptr, size_t n) {
   *ptr = nullptr;
   if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc((void **)ptr, n * sizeof(T));
+  // stream-ordered allocation from the device's default pool (kept warm across handles, see pool_keep_warm)
+  cudaError_t e = cudaMallocAsync((void **)ptr, n * sizeof(T), (cudaStream_t)0);
   if (e != cudaSuccess) {
     g_score_last_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
     return SCORE_ERR_ALLOC;
@@ -98,6 +105,13 @@ int fetch_offsets(const int32_t *src, int n_inst, int64_t total, std::vector<int
 }
 
 int grid_for(long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// Grid of a work-list kernel: at most `per_sm` CTAs per SM (the CTAs loop over the listed work items).
+int wgrid(const ScoreHandle_ *h, long items, int per_sm) {
+  static const int mult = getenv("SCORE_WGRID_MULT") ? atoi(getenv("SCORE_WGRID_MULT")) : 2;  // tuning knob; 0: one item per CTA
+  if (mult <= 0) return (int)std::max(1l, items);
+  return (int)std::max(1l, std::min<long>(items, (long)h->n_sm * per_sm * mult));
+}
 
 // Algorithmic bytes one instance moves through tick kernel `k` in tick mode `mode` (fp64 values, int32
 // indices, every array read or written once; DESIGN.md "algorithmic bytes").  Control kernels read a few
@@ -149,8 +163,9 @@ extern "C" void score_destroy(ScoreHandle h) {
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
   for (auto &e : h->ev_done)
     if (e) cudaEventDestroy(e);
-  for (void *p : h->allocs) cudaFree(p);
-  if (h->sort_tmp) cudaFree(h->sort_tmp);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (void *p : h->allocs) cudaFreeAsync(p, (cudaStream_t)0);
+  if (h->sort_tmp) cudaFreeAsync(h->sort_tmp, (cudaStream_t)0);
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -159,9 +174,109 @@ extern "C" void score_destroy(ScoreHandle h) {
 // Static sorted lists for the coarse-matrix build (coarse.cuh): per instance, the incidences (range,
 // endpoint) sorted by slot and the ranges sorted by (lower slot, higher slot), both by stable counting
 // sorts, the run tables, and the split of the off-diagonal runs over the 32 warps of the build CTA.
+// Instances are independent: they are processed by a pool of host threads and concatenated afterwards.
+struct CoarseInstTables {
+  std::vector<int> inc_code, drun_slot, drun_begin, pr_code, orun_lo, orun_hi, orun_begin, ws;
+  std::vector<double> inc_w2;
+  bool bad = false;
+};
+
+static void coarse_tables_one(const ScoreHandle_ *h, int i, const int *rng_a, const int *rng_b, const double *rng_w,
+                              const int *seg_ptr, CoarseInstTables &out) {
+  constexpr int NW = kCoarseThreads / 32;
+  const int blk = h->P.blk;
+  out.ws.assign(NW + 1, 0);
+  if (h->c_n[i] <= 0) return;
+  const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
+  const int nsegfree = h->c_nb[i] / blk, nslots = nsegfree + Li;
+  const int k0 = h->rng_off[i], Ki = h->rng_off[i + 1] - k0;
+  std::vector<int> pose_slot(Pi, -1), cnt, pos, sa_v(Ki), sb_v(Ki);
+  for (int s = h->seg_begin[i]; s < h->seg_begin[i + 1]; ++s)
+    for (int p = seg_ptr[s]; p < seg_ptr[s + 1]; ++p) pose_slot[p - h->pose_off[i]] = s - h->seg_begin[i] - 1;
+  auto slot_of = [&](int owner) { return owner < Pi ? pose_slot[owner] : nsegfree + (owner - Pi); };
+  // incidences by slot
+  cnt.assign(nslots + 1, 0);
+  for (int k = 0; k < Ki; ++k) {
+    const int a = rng_a[k0 + k], b = rng_b[k0 + k];
+    if (a < 0 || b < 0 || a >= Pi + Li || b >= Pi + Li) {
+      out.bad = true;
+      return;
+    }
+    const int sa = slot_of(a), sb = slot_of(b);
+    sa_v[k] = sa;
+    sb_v[k] = sb;
+    if (sa >= 0 && sa == sb) {
+      cnt[sa + 1]++;
+    } else {
+      if (sa >= 0) cnt[sa + 1]++;
+      if (sb >= 0) cnt[sb + 1]++;
+    }
+  }
+  for (int s = 0; s < nslots; ++s) cnt[s + 1] += cnt[s];
+  const int ninc = cnt[nslots];
+  out.inc_code.resize(ninc);
+  out.inc_w2.resize(ninc);
+  for (int s = 0; s < nslots; ++s)
+    if (cnt[s + 1] > cnt[s]) {
+      out.drun_slot.push_back(s);
+      out.drun_begin.push_back(cnt[s]);
+    }
+  pos.assign(cnt.begin(), cnt.end() - 1);
+  auto put_inc = [&](int s, int k, int e) {
+    const int j = pos[s]++;
+    out.inc_code[j] = (k << 2) | e;
+    out.inc_w2[j] = 2.0 * rng_w[k0 + k];
+  };
+  for (int k = 0; k < Ki; ++k) {
+    const int sa = sa_v[k], sb = sb_v[k];
+    if (sa >= 0 && sa == sb) {
+      put_inc(sa, k, 2);
+    } else {
+      if (sa >= 0) put_inc(sa, k, 0);
+      if (sb >= 0) put_inc(sb, k, 1);
+    }
+  }
+  // ranges by slot pair
+  const size_t nbins = (size_t)nslots * nslots;
+  cnt.assign(nbins + 1, 0);
+  for (int k = 0; k < Ki; ++k) {
+    const int sa = sa_v[k], sb = sb_v[k];
+    if (sa < 0 || sb < 0 || sa == sb) continue;
+    cnt[(size_t)std::min(sa, sb) * nslots + std::max(sa, sb) + 1]++;
+  }
+  for (size_t q = 0; q < nbins; ++q) cnt[q + 1] += cnt[q];
+  const int npair = cnt[nbins];
+  out.pr_code.resize(npair);
+  for (int lo = 0; lo < nslots; ++lo)
+    for (int hi = lo + 1; hi < nslots; ++hi) {
+      const size_t q = (size_t)lo * nslots + hi;
+      if (cnt[q + 1] > cnt[q]) {
+        out.orun_lo.push_back(lo);
+        out.orun_hi.push_back(hi);
+        out.orun_begin.push_back(cnt[q]);
+      }
+    }
+  pos.assign(cnt.begin(), cnt.end() - 1);
+  for (int k = 0; k < Ki; ++k) {
+    const int sa = sa_v[k], sb = sb_v[k];
+    if (sa < 0 || sb < 0 || sa == sb) continue;
+    const size_t q = (size_t)std::min(sa, sb) * nslots + std::max(sa, sb);
+    out.pr_code[pos[q]++] = (k << 1) | (sb < sa ? 1 : 0);
+  }
+  // contiguous, entry-balanced split of the off-diagonal runs over the warps (local run indices)
+  const int nrun = (int)out.orun_lo.size();
+  int w = 0;
+  for (int r = 0; r < nrun; ++r) {
+    const long long done = out.orun_begin[r];
+    while (w < NW && done * NW >= (long long)(w + 1) * npair) out.ws[++w] = r;
+  }
+  while (w < NW) out.ws[++w] = nrun;
+  out.ws[0] = 0;
+}
+
 static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
   DevProblem &P = h->P;
-  const int NI = P.n_inst, blk = P.blk;
+  const int NI = P.n_inst;
   constexpr int NW = kCoarseThreads / 32;
   std::vector<int> rng_a(P.K), rng_b(P.K), seg_ptr(P.n_seg + 1);
   std::vector<double> rng_w(P.K);
@@ -171,115 +286,49 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
     SCORE_CUDA_CHECK(cudaMemcpy(rng_w.data(), desc->rng_w, sizeof(double) * P.K, cudaMemcpyDefault));
   }
   SCORE_CUDA_CHECK(cudaMemcpy(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1), cudaMemcpyDefault));
-  std::vector<int> inc_off(NI + 1, 0), inc_code, drun_off(NI + 1, 0), drun_slot, drun_begin;
-  std::vector<double> inc_w2;
-  std::vector<int> pr_off(NI + 1, 0), pr_code, orun_lo, orun_hi, orun_begin, owarp((size_t)NI * (NW + 1), 0);
-  inc_code.reserve(2 * (size_t)P.K);
-  inc_w2.reserve(2 * (size_t)P.K);
-  pr_code.reserve(P.K);
-  std::vector<int> pose_slot, cnt, pos, sa_v, sb_v;
-  for (int i = 0; i < NI; ++i) {
-    inc_off[i] = (int)inc_code.size();
-    pr_off[i] = (int)pr_code.size();
-    drun_off[i] = (int)drun_slot.size();
-    int *ws = &owarp[(size_t)i * (NW + 1)];
-    for (int w = 0; w <= NW; ++w) ws[w] = (int)orun_lo.size();
-    if (h->c_n[i] <= 0) continue;
-    const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
-    const int nsegfree = h->c_nb[i] / blk, nslots = nsegfree + Li;
-    const int k0 = h->rng_off[i], Ki = h->rng_off[i + 1] - k0;
-    pose_slot.assign(Pi, -1);
-    for (int s = h->seg_begin[i]; s < h->seg_begin[i + 1]; ++s)
-      for (int p = seg_ptr[s]; p < seg_ptr[s + 1]; ++p) pose_slot[p - h->pose_off[i]] = s - h->seg_begin[i] - 1;
-    auto slot_of = [&](int owner) { return owner < Pi ? pose_slot[owner] : nsegfree + (owner - Pi); };
-    sa_v.resize(Ki);
-    sb_v.resize(Ki);
-    // incidences by slot
-    cnt.assign(nslots + 1, 0);
-    for (int k = 0; k < Ki; ++k) {
-      const int a = rng_a[k0 + k], b = rng_b[k0 + k];
-      if (a < 0 || b < 0 || a >= Pi + Li || b >= Pi + Li) {
-        g_score_last_error = "range endpoint out of bounds";
-        return SCORE_ERR_INVALID;
-      }
-      const int sa = slot_of(a), sb = slot_of(b);
-      sa_v[k] = sa;
-      sb_v[k] = sb;
-      if (sa >= 0 && sa == sb) {
-        cnt[sa + 1]++;
-      } else {
-        if (sa >= 0) cnt[sa + 1]++;
-        if (sb >= 0) cnt[sb + 1]++;
-      }
-    }
-    for (int s = 0; s < nslots; ++s) cnt[s + 1] += cnt[s];
-    const int base = (int)inc_code.size(), ninc = cnt[nslots];
-    inc_code.resize(base + ninc);
-    inc_w2.resize(base + ninc);
-    for (int s = 0; s < nslots; ++s)
-      if (cnt[s + 1] > cnt[s]) {
-        drun_slot.push_back(s);
-        drun_begin.push_back(base + cnt[s]);
-      }
-    pos.assign(cnt.begin(), cnt.end() - 1);
-    auto put_inc = [&](int s, int k, int e) {
-      const int j = base + pos[s]++;
-      inc_code[j] = (k << 2) | e;
-      inc_w2[j] = 2.0 * rng_w[k0 + k];
+  std::vector<CoarseInstTables> tabs(NI);
+  {
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+      for (int i = next.fetch_add(1); i < NI; i = next.fetch_add(1))
+        coarse_tables_one(h, i, rng_a.data(), rng_b.data(), rng_w.data(), seg_ptr.data(), tabs[i]);
     };
-    for (int k = 0; k < Ki; ++k) {
-      const int sa = sa_v[k], sb = sb_v[k];
-      if (sa >= 0 && sa == sb) {
-        put_inc(sa, k, 2);
-      } else {
-        if (sa >= 0) put_inc(sa, k, 0);
-        if (sb >= 0) put_inc(sb, k, 1);
-      }
-    }
-    // ranges by slot pair
-    cnt.assign((size_t)nslots * nslots + 1, 0);
-    for (int k = 0; k < Ki; ++k) {
-      const int sa = sa_v[k], sb = sb_v[k];
-      if (sa < 0 || sb < 0 || sa == sb) continue;
-      cnt[(size_t)std::min(sa, sb) * nslots + std::max(sa, sb) + 1]++;
-    }
-    for (size_t q = 0; q < (size_t)nslots * nslots; ++q) cnt[q + 1] += cnt[q];
-    const int pbase = (int)pr_code.size(), npair = cnt[(size_t)nslots * nslots];
-    pr_code.resize(pbase + npair);
-    const int run0 = (int)orun_lo.size();
-    for (int lo = 0; lo < nslots; ++lo)
-      for (int hi = lo + 1; hi < nslots; ++hi) {
-        const size_t q = (size_t)lo * nslots + hi;
-        if (cnt[q + 1] > cnt[q]) {
-          orun_lo.push_back(lo);
-          orun_hi.push_back(hi);
-          orun_begin.push_back(pbase + cnt[q]);
-        }
-      }
-    pos.assign(cnt.begin(), cnt.end() - 1);
-    for (int k = 0; k < Ki; ++k) {
-      const int sa = sa_v[k], sb = sb_v[k];
-      if (sa < 0 || sb < 0 || sa == sb) continue;
-      const size_t q = (size_t)std::min(sa, sb) * nslots + std::max(sa, sb);
-      pr_code[pbase + pos[q]++] = (k << 1) | (sb < sa ? 1 : 0);
-    }
-    // contiguous, entry-balanced split of the off-diagonal runs over the warps
-    const int nrun = (int)orun_lo.size() - run0;
-    int w = 0;
-    for (int r = 0; r < nrun; ++r) {
-      const long long done = orun_begin[run0 + r] - pbase;
-      while (w < NW && done * NW >= (long long)(w + 1) * npair) ws[++w] = run0 + r;
-    }
-    while (w < NW) ws[++w] = run0 + nrun;
-    ws[0] = run0;
+    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, NI / 8 + 1}));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
   }
-  inc_off[NI] = (int)inc_code.size();
-  pr_off[NI] = (int)pr_code.size();
-  drun_off[NI] = (int)drun_slot.size();
-  drun_begin.push_back((int)inc_code.size());
-  orun_begin.push_back((int)pr_code.size());
-  P.c_ninc = (int)inc_code.size();
-  P.c_npair = (int)pr_code.size();
+  std::vector<int> inc_off(NI + 1, 0), drun_off(NI + 1, 0), pr_off(NI + 1, 0), orun_off(NI + 1, 0);
+  for (int i = 0; i < NI; ++i) {
+    if (tabs[i].bad) {
+      g_score_last_error = "range endpoint out of bounds";
+      return SCORE_ERR_INVALID;
+    }
+    inc_off[i + 1] = inc_off[i] + (int)tabs[i].inc_code.size();
+    drun_off[i + 1] = drun_off[i] + (int)tabs[i].drun_slot.size();
+    pr_off[i + 1] = pr_off[i] + (int)tabs[i].pr_code.size();
+    orun_off[i + 1] = orun_off[i] + (int)tabs[i].orun_lo.size();
+  }
+  std::vector<int> inc_code(inc_off[NI]), drun_slot(drun_off[NI]), drun_begin(drun_off[NI] + 1), pr_code(pr_off[NI]);
+  std::vector<int> orun_lo(orun_off[NI]), orun_hi(orun_off[NI]), orun_begin(orun_off[NI] + 1), owarp((size_t)NI * (NW + 1));
+  std::vector<double> inc_w2(inc_off[NI]);
+  for (int i = 0; i < NI; ++i) {
+    const CoarseInstTables &t = tabs[i];
+    std::copy(t.inc_code.begin(), t.inc_code.end(), inc_code.begin() + inc_off[i]);
+    std::copy(t.inc_w2.begin(), t.inc_w2.end(), inc_w2.begin() + inc_off[i]);
+    std::copy(t.pr_code.begin(), t.pr_code.end(), pr_code.begin() + pr_off[i]);
+    std::copy(t.drun_slot.begin(), t.drun_slot.end(), drun_slot.begin() + drun_off[i]);
+    std::copy(t.orun_lo.begin(), t.orun_lo.end(), orun_lo.begin() + orun_off[i]);
+    std::copy(t.orun_hi.begin(), t.orun_hi.end(), orun_hi.begin() + orun_off[i]);
+    for (size_t r = 0; r < t.drun_begin.size(); ++r) drun_begin[drun_off[i] + r] = inc_off[i] + t.drun_begin[r];
+    for (size_t r = 0; r < t.orun_begin.size(); ++r) orun_begin[orun_off[i] + r] = pr_off[i] + t.orun_begin[r];
+    for (int w = 0; w <= NW; ++w) owarp[(size_t)i * (NW + 1) + w] = orun_off[i] + t.ws[w];
+  }
+  drun_begin[drun_off[NI]] = inc_off[NI];
+  orun_begin[orun_off[NI]] = pr_off[NI];
+  P.c_ninc = inc_off[NI];
+  P.c_npair = pr_off[NI];
   int rc;
   const int d1 = P.d + 1;
   if ((rc = upload(h, &P.c_inc_off, inc_off.data(), inc_off.size()))) return rc;
@@ -330,6 +379,14 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   }
   SCORE_CUDA_CHECK(cudaSetDevice(device));
   h->device = device;
+  {
+    // keep freed blocks in the pool instead of returning them to the OS: create/destroy cycles of similar
+    // problems (sweeps) then cost no cudaMalloc / cudaFree at all
+    cudaMemPool_t pool;
+    SCORE_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    SCORE_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   DevProblem &P = h->P;
   P.d = d;
   P.blk = (int)blk;
@@ -507,6 +564,30 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   if ((rc = upload(h, &h->T.cb, cb.data(), cb.size()))) return rc;
   if ((rc = upload(h, &h->T.rb_begin, h->rb_begin.data(), NI + 1))) return rc;
   if ((rc = upload(h, &h->T.cb_begin, h->cb_begin.data(), NI + 1))) return rc;
+  {
+    // work lists: [par, ticket, cnt x6, cnt_ev, pad] + 7 lists of n_inst entries
+    int maxrb = 1, maxcb = 1, maxseg = 1;
+    for (int i = 0; i < NI; ++i) {
+      maxrb = std::max(maxrb, h->rb_begin[i + 1] - h->rb_begin[i]);
+      maxcb = std::max(maxcb, h->cb_begin[i + 1] - h->cb_begin[i]);
+      maxseg = std::max(maxseg, h->seg_begin[i + 1] - h->seg_begin[i]);
+    }
+    DA(h->wl_mem, 16 + 7 * (size_t)NI)
+    WorkLists &W = h->W;
+    W.par = h->wl_mem;
+    W.ticket = h->wl_mem + 1;
+    W.cnt = h->wl_mem + 2;
+    W.cnt_ev = h->wl_mem + 8;
+    W.lists = h->wl_mem + 16;
+    W.ev = W.lists + (size_t)6 * NI;
+    W.n_inst = NI;
+    W.maxrb = maxrb;
+    W.maxcb = maxcb;
+    W.maxseg = maxseg;
+    cudaDeviceProp prop;
+    SCORE_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+  }
   DA(V.part_row, rb.size())
   DA(V.part_ls, rb.size() * kLsSums)
   DA(V.part_upd, rb.size() * 2)
@@ -527,7 +608,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
   SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, P.cols, h->sort_keys, h->sort_idx,
                                                    h->sort_perm, P.nnz, 0, end_bit, (cudaStream_t)0));
-  SCORE_CUDA_CHECK(cudaMalloc(&h->sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 1));
+  SCORE_CUDA_CHECK(cudaMallocAsync(&h->sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 1, (cudaStream_t)0));
   SCORE_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   SCORE_CUDA_CHECK(cudaDeviceSynchronize());
   return SCORE_OK;
@@ -607,7 +688,7 @@ static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStrea
   const int ts = coarse_tile_size(h->c_nmax);
   const size_t smem = coarse_smem_bytes_d<D>(ts);
 #define SCORE_CB(TS) \
-  k_coarse_build<D, TS><<<P.n_inst, kCoarseThreads, smem, st>>>(P, h->V, h->st, cfg.coarse_reg, cfg.coarse_every)
+  k_coarse_build<D, TS><<<wgrid(h, P.n_inst, 1), kCoarseThreads, smem, st>>>(P, h->V, h->st, cfg.coarse_reg, cfg.coarse_every, h->W)
   switch (ts) {
     case 1: SCORE_CB(1); break;
     case 2: SCORE_CB(2); break;
@@ -622,13 +703,13 @@ template <int D>
 static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
   const DevProblem &P = h->P;
   if (pf) pf->mark(KI_PRECOND_REV);
-  k_precond_rev<D><<<P.n_seg + P.n_inst, kSegThreads, 0, st>>>(P, h->V, h->st);
+  k_precond_rev<D><<<wgrid(h, (long)P.n_inst * (h->W.maxseg + 1), 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W);
   if (h->c_nmax > 0) {
     if (pf) pf->mark(KI_COARSE_APPLY);
-    k_coarse_apply<D><<<P.n_inst, kCoarseApplyThreads, 0, st>>>(P, h->V, h->st);
+    k_coarse_apply<D><<<wgrid(h, P.n_inst, 8), kCoarseApplyThreads, 0, st>>>(P, h->V, h->st, h->W);
   }
   if (pf) pf->mark(KI_PRECOND_FWD);
-  k_precond_fwd<D><<<P.n_seg, kSegThreads, 0, st>>>(P, h->V, h->st);
+  k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W);
   return 2 + (h->c_nmax > 0 ? 1 : 0);
 }
 
@@ -639,13 +720,13 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   const DevProblem &P = h->P;
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
-  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (pf) pf->mark(KI_LINESEARCH);
-  k_linesearch<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  k_linesearch<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 3), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, P.n_inst);
+  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, h->W, TM_LS);
   if (pf) pf->mark(KI_ROWUPDATE);
-  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
+  k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
   n += 4;
   if (h->c_nmax > 0) {
     if (pf) pf->mark(KI_COARSE_BUILD);
@@ -653,12 +734,12 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
     n += 1;
   }
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS);
+  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
   n += 1 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS, h->W);
   if (pf) pf->mark(KI_PUPDATE);
-  k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
+  k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
   if (pf) pf->mark(-1);
   return n + 2;
 }
@@ -668,11 +749,11 @@ template <int D>
 static int launch_eval_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
   const DevProblem &P = h->P;
   if (pf) pf->mark(KI_ROWUPDATE);
-  k_rowupdate<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL);
+  k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL);
+  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL, h->W);
   if (pf) pf->mark(-1);
   return 3;
 }
@@ -683,16 +764,16 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   const DevProblem &P = h->P;
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
-  k_rowpass<D><<<h->T.n_rb, kThreads, 0, st>>>(P, h->V, h->T, h->st);
+  k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, P.n_inst);
+  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, h->W, TM_CG);
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<h->T.n_cb, kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_CG);
+  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_CG, h->W);
   n += 3 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<grid_for(P.n_inst, kSegThreads / 32), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG, h->W);
   if (pf) pf->mark(KI_PUPDATE);
-  k_pupdate<<<h->T.n_cb, kThreads, 0, st>>>(h->V, h->T, h->st);
+  k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
   if (pf) pf->mark(-1);
   return n + 2;
 }
@@ -799,6 +880,15 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     }
     SCORE_CUDA_CHECK(cudaMemcpyAsync(h->st, init.data(), sizeof(InstState) * P.n_inst, cudaMemcpyHostToDevice, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(h->d_ndone, 0, sizeof(int), st));
+    {
+      // every instance starts in the line-search phase: run[0] = ls[0] = all instances, parity 0
+      std::vector<int> wl(16 + 2 * (size_t)P.n_inst, 0);
+      wl[2 + 0 * 3 + WL_RUN] = P.n_inst;
+      wl[2 + 0 * 3 + WL_LS] = P.n_inst;
+      for (int i = 0; i < P.n_inst; ++i) wl[16 + i] = wl[16 + P.n_inst + i] = i;
+      SCORE_CUDA_CHECK(cudaMemcpyAsync(h->wl_mem, wl.data(), sizeof(int) * wl.size(), cudaMemcpyHostToDevice, st));
+      SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     SCORE_CUDA_CHECK(cudaStreamSynchronize(st));  // init vector is on the host stack
   }
   SCORE_CUDA_CHECK(cudaEventRecord(ev[2], st));

@@ -116,15 +116,14 @@ __device__ __forceinline__ int coarse_index(int slot, int nsegfree, int nb, int 
 
 // Build + invert.  One CTA (1024 threads) per instance that is in a line-search tick.
 template <int D, int TS>
-__global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, SolverVecs V, InstState *st, double reg,
-                                                                int every) {
+__device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, InstState *st, double reg, int every,
+                                                  const int inst) {
   using CD = CoarseDims<D>;
   constexpr int D1 = CD::D1, BLK = CD::BLK, NM = CD::NM, NH = CD::NH, SB = CD::SB;
   constexpr int NP = 32 * TS;  // padded matrix dimension
   constexpr int NS = NP + 1;   // shared-memory row stride (odd: transposed reads are bank-conflict free)
   constexpr int NW = kCoarseThreads / 32;
   extern __shared__ double sm[];
-  const int inst = blockIdx.x;
   const int n = P.c_n[inst];
   if (n <= 0 || n > NP || st[inst].phase != PH_LS || st[inst].eval_now) return;
   // lagged coarse level: within one barrier stage the inverse is reused for `every` Newton steps
@@ -347,6 +346,18 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
   }
 }
 
+template <int D, int TS>
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, SolverVecs V, InstState *st, double reg,
+                                                                int every, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_LS, act, n_act);
+  for (int ai = blockIdx.x; ai < n_act; ai += gridDim.x) {
+    coarse_build_body<D, TS>(P, V, st, reg, every, act[ai]);
+    __syncthreads();  // shared matrix / staging are reused by the next instance
+  }
+}
+
 template <int D>
 inline size_t coarse_smem_bytes_d(int ts) {
   const size_t np = 32 * (size_t)ts;
@@ -358,12 +369,11 @@ inline int coarse_tile_size(int nmax) { return (nmax + 31) / 32; }
 // y = A_c^-1 c ;  scatter: segment bases -> ytmp (start value of the forward prefix sum), landmarks -> s.
 constexpr int kCoarseApplyThreads = 256;
 template <int D>
-__global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem P, SolverVecs V, const InstState *st) {
+__device__ __forceinline__ void coarse_apply_body(DevProblem P, SolverVecs V, const InstState *st, const int inst) {
   constexpr int BLK = D * (D + 1);
   constexpr int NW = kCoarseApplyThreads / 32;
   __shared__ double red[NW];
   __shared__ double cs[kCoarseMax], ys[kCoarseMax];
-  const int inst = blockIdx.x;
   const int n = P.c_n[inst];
   if (n <= 0 || st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
@@ -383,7 +393,8 @@ __global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) a[t] = warp_sum(a[t]);
-    if (lane < 4 && i + lane < n) ys[i + lane] = a[lane & 3];
+    const double mine = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
+    if (lane < 4 && i + lane < n) ys[i + lane] = mine;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += kCoarseApplyThreads) y[i] = ys[i];
@@ -404,6 +415,18 @@ __global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem
   }
   const double tot = block_sum<kCoarseApplyThreads>(acc, red);
   if (threadIdx.x == 0) V.part_lm[inst] = tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem P, SolverVecs V, const InstState *st,
+                                                                     WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (int ai = blockIdx.x; ai < n_act; ai += gridDim.x) {
+    coarse_apply_body<D>(P, V, st, act[ai]);
+    __syncthreads();
+  }
 }
 
 }  // namespace score

@@ -107,6 +107,36 @@ struct BlockTables {
   int *rb_begin, *cb_begin;  // [n_inst+1]
 };
 
+// Compacted lists of the instances a tick has work for, rebuilt on the device by k_ctrl_b at the end of every
+// tick (double-buffered by parity).  Worker kernels are launched with a fixed, SM-sized grid and loop over
+// (listed instance) x (block of that instance), so finished / idle instances cost nothing.
+//   run:  instances inside a Newton solve or about to take a line-search tick (PH_CG, PH_LS)
+//   ls:   the PH_LS subset (line-search kernels)
+//   wait: PH_WAIT instances (only the controller visits them, to wake them at the next line-search tick)
+//   ev:   instances that asked for a certificate evaluation in this cycle's evaluation tick
+enum ListKind : int { WL_RUN = 0, WL_LS = 1, WL_WAIT = 2, WL_EVAL = 3 };
+struct WorkLists {
+  int *par;     // [1] parity of the lists the workers read
+  int *ticket;  // [1] completion ticket of the k_ctrl_b CTAs (the last one flips the parity)
+  int *cnt;     // [2][3] entries of run / ls / wait per parity
+  int *cnt_ev;  // [1]
+  int *lists;   // [2][3][n_inst] run / ls / wait per parity, then [n_inst] ev   (flat: no dynamic indexing of
+  int *ev;      //  kernel-parameter arrays, which would force a local-memory copy of the parameters)
+  int n_inst;
+  int maxrb, maxcb, maxseg;  // most row blocks / column blocks / chain segments any instance has
+  __device__ __forceinline__ int *list(int parity, int kind) const { return lists + (size_t)(parity * 3 + kind) * n_inst; }
+};
+__device__ __forceinline__ void wl_get(const WorkLists &W, int kind, const int *&list, int &n) {
+  if (kind == WL_EVAL) {
+    list = W.ev;
+    n = *W.cnt_ev;
+    return;
+  }
+  const int p = *W.par;
+  n = W.cnt[p * 3 + kind];
+  list = W.list(p, kind);
+}
+
 struct SolverCfg {
   int max_newton, max_cg;
   double kkt_tol, forcing;

@@ -220,13 +220,12 @@ __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], do
 // With the coarse level on, the base block S_first goes to the coarse right-hand side instead.
 // CTA per chain segment; CTAs past n_seg handle the landmark block of one instance each.
 template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, SolverVecs V, const InstState *st) {
+__device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, const InstState *st, int s) {
   constexpr int D1 = D + 1, NV = D * D1;
   __shared__ double wtot[kSegThreads / 32][NV];
   __shared__ double carry[NV];
   __shared__ double red[kSegThreads / 32];
   const int tid = threadIdx.x;
-  int s = blockIdx.x;
   if (s >= P.n_seg) {
     const int inst = s - P.n_seg;
     if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
@@ -312,15 +311,32 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, Solve
   }
 }
 
+// Listed instance x (its chain segments, then its landmark block: slot W.maxseg).
+template <int D>
+__global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  const int per = W.maxseg + 1;
+  for (long long item = blockIdx.x; item < (long long)n_act * per; item += gridDim.x) {
+    const int inst = act[item / per], j = (int)(item % per);
+    if (j == W.maxseg) {
+      precond_rev_body<D>(P, V, st, P.n_seg + inst);
+    } else if (P.seg_begin[inst] + j < P.seg_begin[inst + 1]) {
+      precond_rev_body<D>(P, V, st, P.seg_begin[inst] + j);
+    }
+    __syncthreads();  // the scan's shared carry is reused by the next item
+  }
+}
+
 // ---- s = P r, pass 2 (forward): Xh_p = sum_{q<=p} Y_q ;  s_p = Xh_p G_p ;  partial r.s
 template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st) {
+__device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s) {
   constexpr int D1 = D + 1, NV = D * D1;
   __shared__ double wtot[kSegThreads / 32][NV];
   __shared__ double carry[NV];
   __shared__ double red[kSegThreads / 32];
   const int tid = threadIdx.x;
-  const int s = blockIdx.x;
   const int inst = P.seg_inst[s];
   if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
@@ -367,6 +383,18 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, Solve
   }
   const double tot = block_sum<kSegThreads>(dot, red);
   if (tid == 0) V.part_seg[s] = tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxseg; item += gridDim.x) {
+    const int inst = act[item / W.maxseg], s = P.seg_begin[inst] + (int)(item % W.maxseg);
+    if (s < P.seg_begin[inst + 1]) precond_fwd_body<D>(P, V, st, s);
+    __syncthreads();
+  }
 }
 
 }  // namespace score

@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(kThreads) k_residual(DevProblem P, const doubl
 // ---- K1: q = B x.  PH_CG: x = p, u = 2 W H_r q (H_r = per-range curvature block tan I + (rad - tan) vv^T/n^2 of
 // F_mu at the current residual, stored as M_k = 2 w H_r by k_rowupdate), partial p'Hp.  PH_LS: x = dz, bdz = q.
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
+__device__ __forceinline__ void rowpass_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
   __shared__ double sq[kRowsPerBlock];
   __shared__ double red[kThreads / 32];
-  const BlockDesc bd = T.rb[blockIdx.x];
+  const BlockDesc bd = T.rb[bid];
   const int phase = st[bd.inst].phase;
   if ((phase != PH_CG && phase != PH_LS) || st[bd.inst].eval_now) return;
   if (phase == PH_LS && st[bd.inst].skip_ls) return;  // start point: no direction yet (bdz stays 0)
@@ -178,15 +178,26 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
     acc += q * u;
   }
   const double tot = block_sum<kThreads>(acc, red);
-  if (threadIdx.x == 0) V.part_row[blockIdx.x] = tot;
+  if (threadIdx.x == 0) V.part_row[bid] = tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
+    const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
+    if (bid < T.rb_begin[inst + 1]) rowpass_body<D>(P, V, T, st, bid);
+  }
 }
 
 // ---- K_ls: F_mu(res + a bdz) at kNumCand step sizes plus a = 0, in one pass.
 // Plain rows are quadratic in a (three sums); range rows are evaluated per candidate.
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st) {
+__device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
   __shared__ double red[kThreads / 32];
-  const BlockDesc bd = T.rb[blockIdx.x];
+  const BlockDesc bd = T.rb[bid];
   const int inst = bd.inst;
   if (st[inst].phase != PH_LS || st[inst].skip_ls || st[inst].eval_now) return;
   const double mu = st[inst].mu;
@@ -233,7 +244,18 @@ __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVec
 #pragma unroll
   for (int i = 0; i < kLsSums; ++i) {
     const double tot = block_sum<kThreads>(sums[i], red);
-    if (threadIdx.x == 0) V.part_ls[(size_t)blockIdx.x * kLsSums + i] = tot;
+    if (threadIdx.x == 0) V.part_ls[(size_t)bid * kLsSums + i] = tot;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_LS, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
+    const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
+    if (bid < T.rb_begin[inst + 1]) linesearch_body<D>(P, V, T, st, bid);
   }
 }
 
@@ -245,10 +267,8 @@ __device__ __forceinline__ double ctrl_sum(const double *part, int i0, int i1, i
   return warp_sum(acc);
 }
 
-// ---- ctrl_a: PCG step length / line-search decision / barrier update.  One warp per instance.
-__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg, int n_inst) {
-  const int inst = blockIdx.x * (kSegThreads / 32) + (threadIdx.x >> 5);
-  if (inst >= n_inst) return;
+// ---- ctrl_a: PCG step length / line-search decision / barrier update.  One warp per listed instance.
+__device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg, const int inst) {
   const int lane = threadIdx.x & 31;
   InstState &S = st[inst];
   const int phase = S.phase;
@@ -305,13 +325,27 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTable
   }
 }
 
+__global__ void __launch_bounds__(kSegThreads) k_ctrl_a(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg, WorkLists W,
+                                                       int mode) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  const int nw = kSegThreads / 32;
+  for (int ai = blockIdx.x * nw + (threadIdx.x >> 5); ai < n_act; ai += gridDim.x * nw) ctrl_a_body(V, T, st, cfg, act[ai]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the lists k_ctrl_b of this tick will fill
+    const int q = (*W.par) ^ 1;
+    W.cnt[q * 3 + 0] = W.cnt[q * 3 + 1] = W.cnt[q * 3 + 2] = 0;
+    if (mode == TM_LS) *W.cnt_ev = 0;
+  }
+}
+
 // ---- K_upd (PH_LS): res += step * bdz ; per-range curvature factors and u = dF_mu/d(res) ; partial F_mu.
 // Evaluation ticks (eval_now): u and sums of the un-smoothed problem (mu = 0) at the current point.
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
-                                                        int mode) {
+__device__ __forceinline__ void rowupdate_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                        int mode, const int bid) {
   __shared__ double red[kThreads / 32];
-  const BlockDesc bd = T.rb[blockIdx.x];
+  const BlockDesc bd = T.rb[bid];
   const int inst = bd.inst;
   const bool eval = mode == TM_EVAL;
   if (st[inst].phase == PH_DONE) return;
@@ -370,17 +404,29 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
   const double Ftot = block_sum<kThreads>(Facc, red);
   const double dtot = block_sum<kThreads>(dacc, red);
   if (threadIdx.x == 0) {
-    V.part_upd[(size_t)blockIdx.x * 2 + 0] = Ftot;
-    V.part_upd[(size_t)blockIdx.x * 2 + 1] = dtot;
+    V.part_upd[(size_t)bid * 2 + 0] = Ftot;
+    V.part_upd[(size_t)bid * 2 + 1] = dtot;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                        int mode, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, mode == TM_EVAL ? WL_EVAL : WL_LS, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
+    const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
+    if (bid < T.rb_begin[inst + 1]) rowupdate_body<D>(P, V, T, st, mode, bid);
   }
 }
 
 // ---- K2: h = B^T u.  PH_CG: dz += alpha p, r -= alpha h.  PH_LS: z += step dz, dz = 0, r = -h (h is the
 // gradient of F_mu at the new point).  Evaluation ticks: partial |g|^2, g.z, |z|^2 of the true gradient only.
-__global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
-                                                      int mode) {
+__device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                      int mode, const int bid) {
   __shared__ double red[kThreads / 32];
-  const BlockDesc bd = T.cb[blockIdx.x];
+  const BlockDesc bd = T.cb[bid];
   const int inst = bd.inst;
   const int phase = st[inst].phase;
   const bool eval = mode == TM_EVAL;
@@ -430,18 +476,27 @@ __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V
     const double b = block_sum<kThreads>(gz, red);
     const double c = block_sum<kThreads>(zz, red);
     if (threadIdx.x == 0) {
-      V.part_col[(size_t)blockIdx.x * 4 + 0] = a;
-      V.part_col[(size_t)blockIdx.x * 4 + 1] = b;
-      V.part_col[(size_t)blockIdx.x * 4 + 2] = c;
+      V.part_col[(size_t)bid * 4 + 0] = a;
+      V.part_col[(size_t)bid * 4 + 1] = b;
+      V.part_col[(size_t)bid * 4 + 2] = c;
     }
   }
 }
 
+__global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+                                                      int mode, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, mode == TM_EVAL ? WL_EVAL : WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxcb; item += gridDim.x) {
+    const int inst = act[item / W.maxcb], bid = T.cb_begin[inst] + (int)(item % W.maxcb);
+    if (bid < T.cb_begin[inst + 1]) colpass_body(P, V, T, st, mode, bid);
+  }
+}
+
 // ---- ctrl_b: after the preconditioner.  PCG bookkeeping / Newton bookkeeping / termination.
-__global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs V, BlockTables T, InstState *st,
-                                                       SolverCfg cfg, int *n_done, int mode) {
-  const int inst = blockIdx.x * (kSegThreads / 32) + (threadIdx.x >> 5);
-  if (inst >= P.n_inst) return;
+__device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg,
+                                            int *n_done, int mode, const int inst) {
   const int lane = threadIdx.x & 31;
   InstState &S = st[inst];
   const int phase = S.phase;
@@ -518,12 +573,60 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
   S.want_eval = 0;
 }
 
+// One warp per listed instance (run list, plus the waiting instances, or the evaluation list); afterwards the
+// instance is filed into the lists of the next tick, and the last CTA to finish publishes them.
+__global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs V, BlockTables T, InstState *st,
+                                                       SolverCfg cfg, int *n_done, int mode, WorkLists W) {
+  const int nw = kSegThreads / 32, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * nw + (threadIdx.x >> 5), stride = gridDim.x * nw;
+  if (mode == TM_EVAL) {
+    const int n_ev = *W.cnt_ev;
+    for (int ai = gw; ai < n_ev; ai += stride) ctrl_b_body(P, V, T, st, cfg, n_done, mode, W.ev[ai]);
+    return;
+  }
+  const int p = *W.par, q = p ^ 1;
+  const int n_run = W.cnt[p * 3 + WL_RUN], n_wait = W.cnt[p * 3 + WL_WAIT];
+  for (int ai = gw; ai < n_run + n_wait; ai += stride) {
+    const int inst = (ai < n_run) ? W.list(p, WL_RUN)[ai] : W.list(p, WL_WAIT)[ai - n_run];
+    if (ai < n_run) {
+      ctrl_b_body(P, V, T, st, cfg, n_done, mode, inst);
+    } else if (mode == TM_CG_LAST && lane == 0 && st[inst].phase == PH_WAIT) {
+      st[inst].phase = PH_LS;
+      st[inst].skip_ls = 0;
+      st[inst].end_cg = 0;
+    }
+    if (lane == 0) {
+      const int ph = st[inst].phase;
+      if (ph == PH_CG || ph == PH_LS) W.list(q, WL_RUN)[atomicAdd(&W.cnt[q * 3 + WL_RUN], 1)] = inst;
+      if (ph == PH_LS) W.list(q, WL_LS)[atomicAdd(&W.cnt[q * 3 + WL_LS], 1)] = inst;
+      if (ph == PH_WAIT) W.list(q, WL_WAIT)[atomicAdd(&W.cnt[q * 3 + WL_WAIT], 1)] = inst;
+      if (mode == TM_LS && st[inst].eval_now) W.ev[atomicAdd(W.cnt_ev, 1)] = inst;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(W.ticket, 1) == (int)gridDim.x - 1) {
+    *W.ticket = 0;
+    *W.par = q;
+  }
+}
+
 // ---- K4 (PH_CG): p = s + beta p   (beta = 0 right after a Newton step; idempotent across an evaluation tick)
-__global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables T, const InstState *st) {
-  const BlockDesc bd = T.cb[blockIdx.x];
+__device__ __forceinline__ void pupdate_body(SolverVecs V, BlockTables T, const InstState *st, const int bid) {
+  const BlockDesc bd = T.cb[bid];
   if (st[bd.inst].phase != PH_CG) return;
   const double beta = st[bd.inst].beta;
   for (int col = bd.i0 + threadIdx.x; col < bd.i1; col += kThreads) V.p[col] = V.s[col] + beta * V.p[col];
+}
+
+__global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxcb; item += gridDim.x) {
+    const int inst = act[item / W.maxcb], bid = T.cb_begin[inst] + (int)(item % W.maxcb);
+    if (bid < T.cb_begin[inst + 1]) pupdate_body(V, T, st, bid);
+  }
 }
 
 }  // namespace score

@@ -411,3 +411,32 @@ def concat(problems: Sequence[LoweredProblem]) -> LoweredProblem:
         landmark_names=[n for p in problems for n in p.landmark_names],
         range_keys=[n for p in problems for n in p.range_keys],
     )
+
+
+def slice_instances(prob: LoweredProblem, i0: int, i1: int) -> LoweredProblem:
+    """Instances [i0, i1) of a batch as a batch of their own (inverse of ``concat``)."""
+    if not (0 <= i0 < i1 <= prob.n_instances):
+        raise ValueError("bad instance range")
+    d = prob.dim
+    p0, p1 = int(prob.pose_off[i0]), int(prob.pose_off[i1])
+    e0, e1 = int(prob.edge_off[i0]), int(prob.edge_off[i1])
+    k0, k1 = int(prob.rng_off[i0]), int(prob.rng_off[i1])
+    q0, q1 = int(prob.prior_off[i0]), int(prob.prior_off[i1])
+    seg_inst = np.asarray(prob.seg_inst)
+    s0, s1 = int(np.searchsorted(seg_inst, i0, side="left")), int(np.searchsorted(seg_inst, i1, side="left"))
+    le = np.asarray(prob.link_edge[p0:p1], np.int64)
+    off = lambda a: (np.asarray(a[i0 : i1 + 1], np.int64) - int(a[i0])).astype(np.int32)
+    names = lambda lst: lst[i0:i1] if len(lst) == prob.n_instances else []
+    return LoweredProblem(
+        dim=d, relaxation=prob.relaxation, n_instances=i1 - i0,
+        pose_off=off(prob.pose_off), lm_off=off(prob.lm_off), edge_off=off(prob.edge_off), rng_off=off(prob.rng_off),
+        prior_off=off(prob.prior_off),
+        seg_ptr=(np.asarray(prob.seg_ptr[s0 : s1 + 1], np.int64) - p0).astype(np.int32),
+        seg_inst=(seg_inst[s0:s1] - i0).astype(np.int32),
+        link_edge=np.where(le >= 0, le - e0, -1).astype(np.int32),
+        edge_i=prob.edge_i[e0:e1], edge_j=prob.edge_j[e0:e1], edge_t=prob.edge_t[e0:e1], edge_R=prob.edge_R[e0:e1],
+        edge_k=prob.edge_k[e0:e1], edge_tau=prob.edge_tau[e0:e1],
+        rng_a=prob.rng_a[k0:k1], rng_b=prob.rng_b[k0:k1], rng_dist=prob.rng_dist[k0:k1], rng_w=prob.rng_w[k0:k1],
+        prior_l=prob.prior_l[q0:q1], prior_t=prob.prior_t[q0:q1], prior_w=prob.prior_w[q0:q1],
+        pose_names=names(prob.pose_names), landmark_names=names(prob.landmark_names), range_keys=names(prob.range_keys),
+    )

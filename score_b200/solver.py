@@ -8,7 +8,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .lowering import QCQP_RELAXATION, LoweredProblem
+from .lowering import QCQP_RELAXATION, LoweredProblem, slice_instances
 
 
 @dataclass
@@ -159,14 +159,24 @@ class ScoreSolver:
         )
         return self.last_stats
 
-    def solution(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
-        """(pose_blocks [P,d,d+1], pose_rounded [P,d,d], landmarks [L,d], dist [K,d] or [K,1])."""
+    def solution_shapes(self):
         p = self.prob
         d = p.dim
-        poses = np.empty((p.P, d, d + 1))
-        rounded = np.empty((p.P, d, d))
-        lms = np.empty((p.L, d))
-        dist = np.empty((p.K, p.dist_per))
+        return (p.P, d, d + 1), (p.P, d, d), (p.L, d), (p.K, p.dist_per)
+
+    def solution(self, out=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """(pose_blocks [P,d,d+1], pose_rounded [P,d,d], landmarks [L,d], dist [K,d] or [K,1]).
+
+        ``out``: optional tuple of four C-contiguous float64 arrays of ``solution_shapes()`` to fill (e.g. views of
+        pinned host memory, which makes the device-to-host copy run at full PCIe speed)."""
+        p = self.prob
+        if out is None:
+            poses, rounded, lms, dist = (np.empty(s) for s in self.solution_shapes())
+        else:
+            poses, rounded, lms, dist = out
+            for a, s in zip(out, self.solution_shapes()):
+                if a.shape != s or a.dtype != np.float64 or not a.flags.c_contiguous:
+                    raise ValueError("solution(out=...): arrays must be C-contiguous float64 of solution_shapes()")
         _check(self._lib.score_get_solution(self._h, poses.ctypes.data, rounded.ctypes.data,
                                             lms.ctypes.data if p.L else None, dist.ctypes.data if p.K else None))
         self.d2h_bytes = poses.nbytes + rounded.nbytes + lms.nbytes + dist.nbytes
@@ -200,6 +210,98 @@ class ScoreSolver:
                                        indptr.ctypes.data, indices.ctypes.data, values.ctypes.data,
                                        weights.ctypes.data, rhs.ctypes.data))
         return indptr, indices, values, weights, rhs, (nr.value, nc.value)
+
+
+class ScoreSolverGroup:
+    """A batch split into ``n_streams`` sub-batches, each with its own handle, CUDA stream and host thread.
+
+    Independent instances never interact, so the sub-batches are solved concurrently: kernels of different
+    streams fill each other's ramp-up / tail gaps on the GPU, and in the create -> solve -> read-back pipeline
+    the host-side upload of one sub-batch overlaps the device-side solve of another (``run_pipelined``).
+    Per-instance results are bit-identical to a single-handle solve (every instance is reduced in fixed order).
+    """
+
+    def __init__(self, prob: LoweredProblem, n_streams: int = 2, device: int = 0, create: bool = True):
+        from concurrent.futures import ThreadPoolExecutor
+
+        n = max(1, min(int(n_streams), prob.n_instances))
+        cuts = [round(j * prob.n_instances / n) for j in range(n + 1)]
+        self.parts = [slice_instances(prob, cuts[j], cuts[j + 1]) for j in range(n)]
+        self.prob, self.device, self.cuts = prob, device, cuts
+        self.pool = ThreadPoolExecutor(n)
+        self.solvers: List[Optional[ScoreSolver]] = [None] * n
+        if create:
+            self.solvers = list(self.pool.map(lambda part: ScoreSolver(part, device=device), self.parts))
+
+    def close(self) -> None:
+        for s in self.solvers:
+            if s is not None:
+                s.close()
+        self.solvers = [None] * len(self.parts)
+        self.pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def merge_stats(stats: List[SolveStats]) -> SolveStats:
+        f = stats[0]
+        summed = lambda name: sum(getattr(s, name) for s in stats)
+        longest = lambda name: max(getattr(s, name) for s in stats)
+        return SolveStats(
+            summed("n_instances"), summed("n_solved"), longest("ticks"), summed("kernel_launches"), longest("assemble_ms"),
+            longest("setup_ms"), longest("solve_ms"), longest("extract_ms"), longest("total_ms"), summed("nnz_reduced"),
+            summed("rows"), summed("cols"), summed("algorithmic_bytes"), np.concatenate([s.instances for s in stats]),
+            kernel_ms=sum(s.kernel_ms for s in stats), profiled_cycles=f.profiled_cycles,
+            kernel_bytes=sum(s.kernel_bytes for s in stats), kernel_count=sum(s.kernel_count for s in stats),
+            kernel_bytes_total=sum(s.kernel_bytes_total for s in stats), cycles=longest("cycles"),
+        )
+
+    def solve(self, **kw) -> SolveStats:
+        kw.pop("stream", None)  # every handle runs on its own (library-owned, non-blocking) stream
+        return self.merge_stats(list(self.pool.map(lambda s: s.solve(**kw), self.solvers)))
+
+    def solution(self, out=None):
+        shapes = self._shapes()
+        if out is None:
+            out = tuple(np.empty(s) for s in shapes)
+        views = self._views(out)
+        list(self.pool.map(lambda a: a[0].solution(out=a[1]), zip(self.solvers, views)))
+        return out
+
+    def _shapes(self):
+        p = self.prob
+        d = p.dim
+        return (p.P, d, d + 1), (p.P, d, d), (p.L, d), (p.K, p.dist_per)
+
+    def _views(self, out):
+        p, c = self.prob, self.cuts
+        views = []
+        for j in range(len(self.parts)):
+            a, b = c[j], c[j + 1]
+            views.append((out[0][p.pose_off[a]:p.pose_off[b]], out[1][p.pose_off[a]:p.pose_off[b]],
+                          out[2][p.lm_off[a]:p.lm_off[b]], out[3][p.rng_off[a]:p.rng_off[b]]))
+        return views
+
+    def run_pipelined(self, out=None, **kw):
+        """create -> solve -> read-back -> destroy of every sub-batch in its own thread (the end-to-end path).
+        Returns (stats, arrays, h2d_bytes, d2h_bytes)."""
+        kw.pop("stream", None)
+        if out is None:
+            out = tuple(np.empty(s) for s in self._shapes())
+        views = self._views(out)
+
+        def one(j):
+            with ScoreSolver(self.parts[j], device=self.device) as s:
+                st = s.solve(**kw)
+                s.solution(out=views[j])
+                return st, s.h2d_bytes, s.d2h_bytes
+
+        res = list(self.pool.map(one, range(len(self.parts))))
+        return self.merge_stats([r[0] for r in res]), out, sum(r[1] for r in res), sum(r[2] for r in res)
 
 
 def round_to_special_orthogonal_batch(mats: np.ndarray, device: int = 0) -> np.ndarray:

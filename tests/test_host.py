@@ -323,3 +323,23 @@ def test_grid3d_generator_and_lowering():
     assert np.array_equal(B.data, prob.B.data) and np.array_equal(w, prob.w)
     with pytest.raises(ValueError):
         generators.grid_3d_arrays(5, n_robots=2, n_steps=3, grid=4, n_landmarks=1, n_ranges=10**6)
+
+
+def test_slice_instances_inverts_concat():
+    import dataclasses
+
+    from score_b200.lowering import slice_instances
+
+    ps = [lower_manhattan_arrays(generators.manhattan_2d_arrays(100 + i, n_robots=2 + i % 3, n_steps=8 + i), "QCQP")
+          for i in range(5)]
+    c = concat(ps)
+    for i0, i1 in [(0, 5), (1, 3), (4, 5), (0, 2)]:
+        a, b = slice_instances(c, i0, i1), concat(ps[i0:i1])
+        for f in dataclasses.fields(a):
+            x, y = getattr(a, f.name), getattr(b, f.name)
+            if isinstance(x, np.ndarray):
+                assert np.array_equal(x, y) and x.dtype == y.dtype, f.name
+            else:
+                assert x == y, f.name
+    with pytest.raises(ValueError):
+        slice_instances(c, 3, 3)
