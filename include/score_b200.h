@@ -170,6 +170,14 @@ int score_get_solution(ScoreHandle h, double *pose_blocks, double *pose_rounded,
 int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
                   int32_t *indptr, int32_t *indices, double *values, double *weights, double *rhs);
 
+/* Row-partitioned multi-GPU solve of ONE large instance (BASELINE configs[4]): every rank creates the
+ * same handle on its own GPU, then joins a communicator; score_solve then splits the measurement rows over the
+ * ranks and sums the B^T u partials (plus the scalar partial sums, in the same buffer) with one NCCL all-reduce per
+ * iteration.  Rank 0 makes the 128-byte id and ships it to the others by any means (the Python wrapper uses
+ * torch.distributed).  The reference has no counterpart (single process). */
+int score_nccl_unique_id(char *out128);
+int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, const char *id128);
+
 /* Test / diagnostic access to solver internals of instance `inst` after score_solve (host buffer of
  * `capacity` doubles; *count receives the number of doubles the array has; pass out = NULL to query):
  *   SCORE_INT_COARSE_INV  nc x nc inverse coarse matrix of the last Newton step (0 doubles: coarse level off)

@@ -124,6 +124,8 @@ EXPORTED_SYMBOLS = [
     "score_get_sizes",
     "score_get_solution",
     "score_get_csr",
+    "score_nccl_unique_id",
+    "score_comm_init",
     "score_get_internal",
     "score_round_so",
     "score_destroy",
@@ -171,6 +173,10 @@ def load() -> C.CDLL:
         C.c_void_p,
     ]
     lib.score_get_csr.restype = C.c_int
+    lib.score_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.score_nccl_unique_id.restype = C.c_int
+    lib.score_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]
+    lib.score_comm_init.restype = C.c_int
     lib.score_get_internal.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.score_get_internal.restype = C.c_int
     lib.score_round_so.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]

@@ -1,4 +1,7 @@
 // libscore_b200 — C ABI (include/score_b200.h) over the sm_100a kernels.
+#include <cusolverDn.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +20,35 @@
 #include "solver.cuh"
 
 thread_local std::string g_score_last_error;
+
+// NCCL is bound at run time, and only when a row-partitioned solve asks for it: the library then shares the
+// process's NCCL (torch's, when torch.distributed brought one) and has no load-time dependency on it.
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+  if (g_nccl.ok) return true;
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    g_score_last_error = std::string("cannot load NCCL: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+  if (!g_nccl.ok) g_score_last_error = "NCCL library lacks a required symbol";
+  return g_nccl.ok;
+}
+}  // namespace
 
 using namespace score;
 
@@ -46,6 +78,18 @@ struct ScoreHandle_ {
   std::vector<int> rb_begin, cb_begin;
   std::vector<int> c_off, c_moff, c_n, c_nb;
   int c_nmax = 0;
+  // row-partitioned multi-GPU solve of one instance (score_comm_init)
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  double *red_send = nullptr, *red_recv = nullptr;  // [part_row n_rb | part_upd 2 n_rb | h nz]
+  double *ls_recv = nullptr, *mk_recv = nullptr;
+  size_t red_count = 0;
+  SolverVecs Vg{};  // V with the reduced (global) partial sums / curvature blocks / h
+  bool c_big = false;  // single instance with kCoarseMax < nc <= kCoarseBigMax: dense global-memory coarse level
+  cusolverDnHandle_t cusolver = nullptr;
+  double *cs_work = nullptr;
+  int cs_lwork = 0;
+  int *cs_info = nullptr;
   std::vector<void *> allocs;
   cudaStream_t own_stream = nullptr;
   SolverCfg graph_cfg{};
@@ -160,6 +204,8 @@ extern "C" const char *score_version(void) { return "score_b200 0.1.0 (sm_100a)"
 extern "C" void score_destroy(ScoreHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  if (h->cusolver) cusolverDnDestroy(h->cusolver);
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
   for (auto &e : h->ev_done)
     if (e) cudaEventDestroy(e);
@@ -343,6 +389,7 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
   if ((rc = upload(h, &P.c_orun_hi, orun_hi.data(), orun_hi.size()))) return rc;
   if ((rc = upload(h, &P.c_orun_begin, orun_begin.data(), orun_begin.size()))) return rc;
   if ((rc = upload(h, &P.c_owarp, owarp.data(), owarp.size()))) return rc;
+  if ((rc = upload(h, &P.c_orun_off, orun_off.data(), orun_off.size()))) return rc;
   if ((rc = dalloc(h, &P.c_inc_h, (size_t)P.c_ninc * d1))) return rc;
   if ((rc = dalloc(h, &P.c_pr_h, (size_t)P.c_npair * 2 * d1))) return rc;
   return SCORE_OK;
@@ -522,7 +569,10 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     for (int i = 0; i < NI; ++i) {
       const int nsegfree = h->seg_begin[i + 1] - h->seg_begin[i] - 1;
       const int nb = nsegfree * (int)blk, nc = nb + (h->lm_off[i + 1] - h->lm_off[i]) * d;
-      const bool on = nc > 0 && nc <= kCoarseMax;
+      const bool small = nc > 0 && nc <= kCoarseMax;
+      const bool big = NI == 1 && nc > kCoarseMax && nc <= kCoarseBigMax;
+      const bool on = small || big;
+      h->c_big = big;
       h->c_n[i] = on ? nc : 0;
       h->c_nb[i] = on ? nb : 0;
       h->c_off[i + 1] = h->c_off[i] + (on ? nc : 0);
@@ -532,7 +582,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
         return SCORE_ERR_INVALID;
       }
       h->c_moff[i + 1] = (int)moff;
-      if (on && nc > h->c_nmax) h->c_nmax = nc;
+      if (small && nc > h->c_nmax) h->c_nmax = nc;
     }
     if ((rc = upload(h, &P.c_off, h->c_off.data(), NI + 1))) return rc;
     if ((rc = upload(h, &P.c_moff, h->c_moff.data(), NI + 1))) return rc;
@@ -588,9 +638,15 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     SCORE_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
   }
-  DA(V.part_row, rb.size())
+  h->red_count = 3 * rb.size() + (size_t)P.nz;
+  DA(h->red_send, h->red_count)
+  V.part_row = h->red_send;
+  V.part_upd = h->red_send + rb.size();
+  V.hloc = h->red_send + 3 * rb.size();
+  V.hglob = V.hloc;
   DA(V.part_ls, rb.size() * kLsSums)
-  DA(V.part_upd, rb.size() * 2)
+  h->W.rb_lo = 0;
+  h->W.rb_hi = (int)rb.size();
   DA(V.part_col, cb.size() * 4)
   DA(V.part_seg, P.n_seg)
   DA(V.part_lm, NI)
@@ -688,7 +744,7 @@ static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStrea
   const int ts = coarse_tile_size(h->c_nmax);
   const size_t smem = coarse_smem_bytes_d<D>(ts);
 #define SCORE_CB(TS) \
-  k_coarse_build<D, TS><<<wgrid(h, P.n_inst, 1), kCoarseThreads, smem, st>>>(P, h->V, h->st, cfg.coarse_reg, cfg.coarse_every, h->W)
+  k_coarse_build<D, TS><<<wgrid(h, P.n_inst, 1), kCoarseThreads, smem, st>>>(P, h->n_ranks > 1 ? h->Vg : h->V, h->st, cfg.coarse_reg, cfg.coarse_every, h->W)
   switch (ts) {
     case 1: SCORE_CB(1); break;
     case 2: SCORE_CB(2); break;
@@ -696,6 +752,28 @@ static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStrea
     default: SCORE_CB(4); break;
   }
 #undef SCORE_CB
+}
+
+// Dense coarse level of a large single instance: accumulate into global memory, Cholesky-factorise and invert
+// with cuSOLVER (plain library calls), mirror to a full symmetric matrix.
+template <int D>
+static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st) {
+  const DevProblem &P = h->P;
+  const int n = h->c_n[0];
+  double *A = P.c_Ainv;
+  SCORE_CUDA_CHECK(cudaMemsetAsync(A, 0, sizeof(double) * (size_t)n * n, st));
+  k_coarse_big_accum<D><<<h->n_sm * 4, kBigThreads, 0, st>>>(P, h->n_ranks > 1 ? h->Vg : h->V, cfg.coarse_reg, A);
+  k_coarse_big_finish<D><<<grid_for(n, 256), 256, 0, st>>>(P, A);
+  // row-major upper triangle == column-major lower triangle
+  if (cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, A, n, h->cs_work, h->cs_lwork, h->cs_info) !=
+          CUSOLVER_STATUS_SUCCESS ||
+      cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, A, n, h->cs_work, h->cs_lwork, h->cs_info) !=
+          CUSOLVER_STATUS_SUCCESS) {
+    g_score_last_error = "cuSOLVER potrf/potri failed on the coarse matrix";
+    return SCORE_ERR_CUDA;
+  }
+  k_mirror_upper<<<grid_for((long)n * n, 256), 256, 0, st>>>(A, n);
+  return SCORE_OK;
 }
 
 // Preconditioner application s = P r (+ partial r.s), shared by the line-search and PCG ticks.
@@ -707,37 +785,83 @@ static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
   if (h->c_nmax > 0) {
     if (pf) pf->mark(KI_COARSE_APPLY);
     k_coarse_apply<D><<<wgrid(h, P.n_inst, 8), kCoarseApplyThreads, 0, st>>>(P, h->V, h->st, h->W);
+  } else if (h->c_big) {
+    if (pf) pf->mark(KI_COARSE_APPLY);
+    k_coarse_big_apply<<<grid_for(h->c_n[0], kBigThreads / 32), kBigThreads, 0, st>>>(P, h->st);
+    k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st);
   }
   if (pf) pf->mark(KI_PRECOND_FWD);
   k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W);
-  return 2 + (h->c_nmax > 0 ? 1 : 0);
+  return 2 + (h->c_nmax > 0 ? 1 : 0) + (h->c_big ? 2 : 0);
+}
+
+// Row-partitioned solve: sum a buffer over the ranks (out of place; every rank contributes its own rows only).
+static void dist_allreduce(ScoreHandle_ *h, const double *send, double *recv, size_t count, cudaStream_t st) {
+  g_nccl.AllReduce(send, recv, count, ncclDouble, ncclSum, h->comm, st);
+}
+
+// h = B^T u and the column-space update.  One fused kernel on a single GPU; with row partitioning the SpMV of
+// the local rows, ONE all-reduce of [partial sums | h] over NVLink, then the update from the summed h.
+static int launch_colpass(ScoreHandle_ *h, cudaStream_t st, int mode) {
+  const DevProblem &P = h->P;
+  const int grid = wgrid(h, (long)P.n_inst * h->W.maxcb, 8);
+  if (h->n_ranks == 1) {
+    k_colpass<<<grid, kThreads, 0, st>>>(P, h->V, h->T, h->st, mode, CS_FUSED, h->W);
+    return 1;
+  }
+  k_colpass<<<grid, kThreads, 0, st>>>(P, h->V, h->T, h->st, mode, CS_SPMV, h->W);
+  dist_allreduce(h, h->red_send, h->red_recv, h->red_count, st);
+  return 2;
+}
+static void launch_colapply(ScoreHandle_ *h, cudaStream_t st, int mode) {
+  const DevProblem &P = h->P;
+  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->Vg, h->T, h->st, mode, CS_APPLY, h->W);
 }
 
 // Line-search tick: step along dz, new residual / gradient / curvature / coarse matrix, first preconditioned
 // residual of the next Newton system.  Returns the number of kernels launched.
 template <int D>
-static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
+static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr,
+                          bool big_build = false) {
   const DevProblem &P = h->P;
+  const bool dist = h->n_ranks > 1;
+  const SolverVecs &Vc = dist ? h->Vg : h->V;  // what the controllers / coarse build read
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
   k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (pf) pf->mark(KI_LINESEARCH);
   k_linesearch<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 3), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  if (dist) {
+    // line-search sums, and p'Hp of an instance that is still inside a Newton solve during this tick
+    dist_allreduce(h, h->V.part_ls, h->ls_recv, (size_t)h->T.n_rb * kLsSums, st);
+    dist_allreduce(h, h->V.part_row, h->Vg.part_row, (size_t)h->T.n_rb, st);
+  }
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, h->W, TM_LS);
+  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(Vc, h->T, h->st, cfg, h->W, TM_LS);
   if (pf) pf->mark(KI_ROWUPDATE);
   k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
   n += 4;
+  const bool build = h->c_nmax > 0 || (h->c_big && big_build);
+  if (dist && build && (h->c_big ? big_build : true))  // every rank needs the curvature blocks of all ranges
+    dist_allreduce(h, h->V.mk, h->mk_recv, (size_t)P.K * (D * (D + 1) / 2), st);
   if (h->c_nmax > 0) {
     if (pf) pf->mark(KI_COARSE_BUILD);
     launch_coarse_build<D>(h, cfg, st);
     n += 1;
+  } else if (h->c_big && big_build) {
+    if (pf) pf->mark(KI_COARSE_BUILD);
+    launch_coarse_big_build<D>(h, cfg, st);
+    n += 4;
   }
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
-  n += 1 + launch_precond<D>(h, st, pf);
+  n += launch_colpass(h, st, TM_LS);
+  if (dist) {
+    launch_colapply(h, st, TM_LS);
+    n += 1;
+  }
+  n += launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_LS, h->W);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, TM_LS, h->W);
   if (pf) pf->mark(KI_PUPDATE);
   k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
   if (pf) pf->mark(-1);
@@ -748,30 +872,48 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
 template <int D>
 static int launch_eval_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
   const DevProblem &P = h->P;
+  const bool dist = h->n_ranks > 1;
+  const SolverVecs &Vc = dist ? h->Vg : h->V;
+  int n = 2;
   if (pf) pf->mark(KI_ROWUPDATE);
   k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
+  n += launch_colpass(h, st, TM_EVAL);
+  if (dist) {
+    launch_colapply(h, st, TM_EVAL);
+    n += 1;
+  }
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_EVAL, h->W);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, TM_EVAL, h->W);
   if (pf) pf->mark(-1);
-  return 3;
+  return n;
 }
 
 // PCG tick: one preconditioned conjugate-gradient iteration of every instance still solving its Newton system.
+// Row-partitioned: the SpMV of B^T runs before the controller so that its partial h and the partial p'Hp travel
+// in the same all-reduce (one collective per PCG iteration).
 template <int D>
 static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, bool last, TickProfiler *pf = nullptr) {
   const DevProblem &P = h->P;
+  const bool dist = h->n_ranks > 1;
+  const SolverVecs &Vc = dist ? h->Vg : h->V;
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
   k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  if (dist) {
+    if (pf) pf->mark(KI_COLPASS);
+    n += launch_colpass(h, st, TM_CG);
+  }
   if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(h->V, h->T, h->st, cfg, h->W, TM_CG);
+  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(Vc, h->T, h->st, cfg, h->W, TM_CG);
   if (pf) pf->mark(KI_COLPASS);
-  k_colpass<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_CG, h->W);
+  if (dist)
+    launch_colapply(h, st, TM_CG);
+  else
+    launch_colpass(h, st, TM_CG);
   n += 3 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
-  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG, h->W);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG, h->W);
   if (pf) pf->mark(KI_PUPDATE);
   k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
   if (pf) pf->mark(-1);
@@ -780,14 +922,16 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
 
 // One cycle = line-search tick + evaluation tick + n_cg PCG ticks.
 template <int D>
-static int launch_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr) {
-  int n = launch_ls_tick<D>(h, cfg, st, pf);
+static int launch_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr,
+                        bool big_build = false) {
+  int n = launch_ls_tick<D>(h, cfg, st, pf, big_build);
   n += launch_eval_tick<D>(h, cfg, st, pf);
   for (int i = 0; i < n_cg; ++i) n += launch_cg_tick<D>(h, cfg, st, i == n_cg - 1, pf);
   return n;
 }
-static int launch_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr) {
-  return h->P.d == 2 ? launch_cycle<2>(h, cfg, st, n_cg, pf) : launch_cycle<3>(h, cfg, st, n_cg, pf);
+static int launch_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr,
+                          bool big_build = false) {
+  return h->P.d == 2 ? launch_cycle<2>(h, cfg, st, n_cg, pf, big_build) : launch_cycle<3>(h, cfg, st, n_cg, pf, big_build);
 }
 
 // PCG ticks of cycle c: `base` early on, doubling every `grow_every` cycles after `grow_after` (the few
@@ -838,14 +982,24 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     AsmOut out{P.indptr, P.cols, P.vals, P.w, P.b, h->nnz_row};
     const long nf = (long)P.E + P.K + P.Lp;
     k_assemble<<<grid_for(nf, 256), 256, 0, st>>>(P, ASM_REDUCED, 0, P.n_inst, out);
-    k_iota<<<grid_for(P.nnz, 256), 256, 0, st>>>(h->sort_idx, P.nnz);
+    // transpose of the rows this rank owns (all rows on a single GPU): entries [nnz_lo, nnz_hi)
+    int nnz_lo = 0, nnz_hi = P.nnz;
+    if (h->n_ranks > 1) {
+      const int row_lo = h->W.rb_lo * kRowsPerBlock, row_hi = std::min(P.m, h->W.rb_hi * kRowsPerBlock);
+      SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_lo, P.indptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_hi, P.indptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const int nloc = nnz_hi - nnz_lo;
+    k_iota<<<grid_for(std::max(nloc, 1), 256), 256, 0, st>>>(h->sort_idx, nloc);
     int end_bit = 1;
     while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
-    SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols, h->sort_keys, h->sort_idx,
-                                                     h->sort_perm, P.nnz, 0, end_bit, st));
+    SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols + nnz_lo, h->sort_keys,
+                                                     h->sort_idx, h->sort_perm, nloc, 0, end_bit, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(P.t_indptr, 0, sizeof(int) * (P.nz + 1), st));
-    k_transpose_fill<<<grid_for(P.nnz, 256), 256, 0, st>>>(P.nnz, P.nz, h->sort_keys, h->sort_perm, h->nnz_row, P.vals,
-                                                           P.t_indptr, P.t_rows, P.t_vals);
+    if (nloc > 0)
+      k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->sort_keys, h->sort_perm, h->nnz_row + nnz_lo,
+                                                            P.vals + nnz_lo, P.t_indptr, P.t_rows, P.t_vals);
     launches += 6;
   }
   SCORE_CUDA_CHECK(cudaEventRecord(ev[1], st));
@@ -853,10 +1007,15 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   {
     k_dead_reckon<<<grid_for(P.n_seg, 64), 64, 0, st>>>(P);
     k_diag_setup<<<grid_for((long)P.P + (long)P.L * d, 256), 256, 0, st>>>(P, h->wsum);
+    if (h->n_ranks > 1) {  // range weights were summed over the local rows only
+      g_nccl.AllReduce(h->wsum, h->wsum, P.P, ncclDouble, ncclSum, h->comm, st);
+      if (P.L > 0) g_nccl.AllReduce(P.lm_inv, P.lm_inv, (size_t)P.L * d, ncclDouble, ncclSum, h->comm, st);
+    }
+    if (P.L > 0) k_lm_finish<<<grid_for((long)P.L * d, 256), 256, 0, st>>>(P);
     k_build_M<<<grid_for(P.P, 128), 128, 0, st>>>(P, h->wsum);
     k_init_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z);
     k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
-    if (h->c_nmax > 0 && std::max(P.c_ninc, P.c_npair) > 0) {
+    if ((h->c_nmax > 0 || h->c_big) && std::max(P.c_ninc, P.c_npair) > 0) {
       if (d == 2)
         k_coarse_static<2><<<grid_for(std::max(P.c_ninc, P.c_npair), 256), 256, 0, st>>>(P);
       else
@@ -869,6 +1028,12 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.u, 0, sizeof(double) * P.m, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.bdz, 0, sizeof(double) * P.m, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(V.part_col, 0, sizeof(double) * 4 * h->T.n_cb, st));
+    if (h->n_ranks > 1) {
+      // rows of other ranks contribute exact zeros to every all-reduce
+      SCORE_CUDA_CHECK(cudaMemsetAsync(h->red_send, 0, sizeof(double) * h->red_count, st));
+      SCORE_CUDA_CHECK(cudaMemsetAsync(V.part_ls, 0, sizeof(double) * (size_t)h->T.n_rb * kLsSums, st));
+      SCORE_CUDA_CHECK(cudaMemsetAsync(V.mk, 0, sizeof(double) * (size_t)P.K * (d * (d + 1) / 2), st));
+    }
     std::vector<InstState> init(P.n_inst);
     memset(init.data(), 0, sizeof(InstState) * P.n_inst);
     for (auto &s : init) {
@@ -928,7 +1093,38 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   TickProfiler pf;
   pf.st = st;
   h->h_ndone[0] = h->h_ndone[1] = 0;
-  while (ticks < max_ticks) {
+  if (h->c_big || h->n_ranks > 1) {
+    // large single instance: cuSOLVER / NCCL are not captured into graphs; cycles are launched directly and the host
+    // decides per cycle whether the line-search tick will rebuild the coarse level (the instance is in PH_LS)
+    if (h->c_big && !h->cusolver) {
+      if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS) {
+        g_score_last_error = "cusolverDnCreate failed";
+        return SCORE_ERR_CUDA;
+      }
+      const int n = h->c_n[0];
+      int l1 = 0, l2 = 0;
+      cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, P.c_Ainv, n, &l1);
+      cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, P.c_Ainv, n, &l2);
+      h->cs_lwork = std::max(l1, l2);
+      if ((rc = dalloc(h, &h->cs_work, (size_t)h->cs_lwork))) return rc;
+      if ((rc = dalloc(h, &h->cs_info, 1))) return rc;
+      SCORE_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    if (h->c_big) cusolverDnSetStream(h->cusolver, st);
+    const int n_cg = cg_base;
+    while (ticks < max_ticks) {
+      InstState s0;
+      SCORE_CUDA_CHECK(cudaMemcpyAsync(&s0, h->st, sizeof(InstState), cudaMemcpyDeviceToHost, st));
+      SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (s0.phase == PH_DONE) break;
+      const bool prof = cycles >= prof_skip && cycles < prof_end;
+      launches += launch_cycle_d(h, cfg, st, n_cg, prof ? &pf : nullptr, s0.phase == PH_LS);
+      if (prof) profiled += 1;
+      ticks += 1 + n_cg;
+      cycles += 1;
+    }
+  }
+  while (!(h->c_big || h->n_ranks > 1) && ticks < max_ticks) {
     const int n_cg = cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
     const bool prof = cycles >= prof_skip && cycles < prof_end;
     if (prof) {
@@ -1157,6 +1353,65 @@ extern "C" int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t
     if (weights) SCORE_CUDA_CHECK(cudaMemcpy(weights, P.w + r0, sizeof(double) * rows, cudaMemcpyDefault));
     if (rhs) SCORE_CUDA_CHECK(cudaMemcpy(rhs, P.b + r0, sizeof(double) * rows, cudaMemcpyDefault));
   }
+  return SCORE_OK;
+}
+
+extern "C" int score_nccl_unique_id(char *out128) {
+  if (!out128) {
+    g_score_last_error = "null argument";
+    return SCORE_ERR_INVALID;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!nccl_load()) return SCORE_ERR_CUDA;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) {
+    g_score_last_error = "ncclGetUniqueId failed";
+    return SCORE_ERR_CUDA;
+  }
+  memcpy(out128, &id, 128);
+  return SCORE_OK;
+}
+
+extern "C" int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, const char *id128) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) {
+    g_score_last_error = "bad argument";
+    return SCORE_ERR_INVALID;
+  }
+  DevProblem &P = h->P;
+  if (P.n_inst != 1) {
+    g_score_last_error = "row partitioning applies to a single instance (batches are sharded by instance)";
+    return SCORE_ERR_INVALID;
+  }
+  if (h->comm) {
+    g_score_last_error = "communicator already initialised";
+    return SCORE_ERR_STATE;
+  }
+  SCORE_CUDA_CHECK(cudaSetDevice(h->device));
+  if (n_ranks == 1) return SCORE_OK;
+  if (!nccl_load()) return SCORE_ERR_CUDA;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (g_nccl.CommInitRank(&h->comm, n_ranks, id, rank) != ncclSuccess) {
+    g_score_last_error = "ncclCommInitRank failed";
+    h->comm = nullptr;
+    return SCORE_ERR_CUDA;
+  }
+  h->n_ranks = n_ranks;
+  h->rank = rank;
+  const int n_rb = h->T.n_rb, d = P.d;
+  h->W.rb_lo = (int)((long long)rank * n_rb / n_ranks);
+  h->W.rb_hi = (int)((long long)(rank + 1) * n_rb / n_ranks);
+  int rc;
+  if ((rc = dalloc(h, &h->red_recv, h->red_count))) return rc;
+  if ((rc = dalloc(h, &h->ls_recv, (size_t)n_rb * kLsSums))) return rc;
+  if ((rc = dalloc(h, &h->mk_recv, (size_t)P.K * (d * (d + 1) / 2)))) return rc;
+  h->Vg = h->V;
+  h->Vg.part_row = h->red_recv;
+  h->Vg.part_upd = h->red_recv + n_rb;
+  h->Vg.hglob = h->red_recv + 3 * (size_t)n_rb;
+  h->Vg.part_ls = h->ls_recv;
+  h->Vg.mk = h->mk_recv;
+  SCORE_CUDA_CHECK(cudaDeviceSynchronize());
   return SCORE_OK;
 }
 

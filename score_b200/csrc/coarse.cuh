@@ -114,35 +114,19 @@ __device__ __forceinline__ int coarse_index(int slot, int nsegfree, int nb, int 
   return (c == D) ? nb + (slot - nsegfree) * D + r : -1;
 }
 
-// Build + invert.  One CTA (1024 threads) per instance that is in a line-search tick.
-template <int D, int TS>
-__device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, InstState *st, double reg, int every,
-                                                  const int inst) {
+// Sum the range contributions into A (row stride lda; zero-initialised by the caller): diagonal blocks from
+// the slot-sorted incidence runs (run r -> warp r mod nw) and upper off-diagonal blocks from the pair-sorted
+// runs.  `wid` / `nw`: this warp's index / the number of cooperating warps; `mystage`: CoarseDims::STAGE
+// doubles of shared memory private to the warp.  Every block has exactly one owning warp.
+template <int D>
+__device__ __forceinline__ void coarse_accumulate(const DevProblem &P, const SolverVecs &V, const int inst, const double reg,
+                                                  double *A, const int lda, const int wid, const int nw,
+                                                  const bool use_owarp, double *mystage) {
   using CD = CoarseDims<D>;
   constexpr int D1 = CD::D1, BLK = CD::BLK, NM = CD::NM, NH = CD::NH, SB = CD::SB;
-  constexpr int NP = 32 * TS;  // padded matrix dimension
-  constexpr int NS = NP + 1;   // shared-memory row stride (odd: transposed reads are bank-conflict free)
-  constexpr int NW = kCoarseThreads / 32;
-  extern __shared__ double sm[];
-  const int n = P.c_n[inst];
-  if (n <= 0 || n > NP || st[inst].phase != PH_LS || st[inst].eval_now) return;
-  // lagged coarse level: within one barrier stage the inverse is reused for `every` Newton steps
-  if (every > 1 && st[inst].mu == st[inst].mu_c && st[inst].c_age < every) {
-    __syncthreads();
-    if (threadIdx.x == 0) st[inst].c_age += 1;
-    return;
-  }
-  double *A = sm;                       // NP x NS
-  double *rowb = A + NP * NS;           // 2 x NP (NP * NS is even: 16-byte aligned)
-  double *pivb = rowb + 2 * NP;         // 2
-  double *stage = pivb + 2;             // NW x STAGE
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i < NP * NS; i += kCoarseThreads) A[i] = 0.0;
-  __syncthreads();
+  const int lane = threadIdx.x & 31;
   const int nb = P.c_nb[inst], nsegfree = nb / BLK;
   const int k0 = P.rng_off[inst];
-  double *mystage = stage + wid * CD::STAGE;
-
   // ---- diagonal blocks: runs of the slot-sorted incidence list, run r -> warp r % NW
   {
     constexpr int NACC = (CD::NPD + 31) / 32;
@@ -157,7 +141,7 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
       pcc[a] = cc;
     }
     const int r0 = P.c_drun_off[inst], r1 = P.c_drun_off[inst + 1];
-    for (int run = r0 + wid; run < r1; run += NW) {
+    for (int run = r0 + wid; run < r1; run += nw) {
       const int slot = P.c_drun_slot[run];
       const int jb = P.c_drun_begin[run], je = P.c_drun_begin[run + 1];
       double acc[NACC];
@@ -199,12 +183,12 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
         const int i2 = coarse_index<D>(slot, nsegfree, nb, r, cc), i3 = coarse_index<D>(slot, nsegfree, nb, rr, c);
         const double v = acc[a];
         if (i0 >= 0 && i1 >= 0) {
-          A[i0 * NS + i1] += v;
-          if (i1 != i0) A[i1 * NS + i0] += v;
+          A[i0 * lda + i1] += v;
+          if (i1 != i0) A[i1 * lda + i0] += v;
         }
         if (c != cc && r != rr && i2 >= 0 && i3 >= 0) {  // (r, c') x (r', c): distinct image only when both differ
-          A[i2 * NS + i3] += v;
-          A[i3 * NS + i2] += v;
+          A[i2 * lda + i3] += v;
+          A[i3 * lda + i2] += v;
         }
       }
     }
@@ -220,9 +204,12 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
       pc[a] = (p / D1) % D1;
       pcc[a] = p % D1;
     }
-    const int *wsplit = P.c_owarp + (size_t)inst * (NW + 1);
-    const int run_b = wsplit[wid], run_e = wsplit[wid + 1];
-    for (int run = run_b; run < run_e; ++run) {
+    // small matrices: the host-balanced contiguous chunk of this warp; big ones: round robin over all warps
+    const int *wsplit = P.c_owarp + (size_t)inst * (kCoarseThreads / 32 + 1);
+    const int run_b = use_owarp ? wsplit[wid] : P.c_orun_off[inst] + wid;
+    const int run_e = use_owarp ? wsplit[wid + 1] : P.c_orun_off[inst + 1];
+    const int run_step = use_owarp ? 1 : nw;
+    for (int run = run_b; run < run_e; run += run_step) {
       const int lo = P.c_orun_lo[run], hi = P.c_orun_hi[run];
       const int jb = P.c_orun_begin[run], je = P.c_orun_begin[run + 1];
       double acc[NACC];
@@ -257,14 +244,44 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
         const int c = pc[a], cc = pcc[a];
         const double v = -acc[a];
         const int i0 = coarse_index<D>(lo, nsegfree, nb, r, c), i1 = coarse_index<D>(hi, nsegfree, nb, rr, cc);
-        if (i0 >= 0 && i1 >= 0) A[i0 * NS + i1] += v;
+        if (i0 >= 0 && i1 >= 0) A[i0 * lda + i1] += v;
         if (r != rr) {
           const int i2 = coarse_index<D>(lo, nsegfree, nb, rr, c), i3 = coarse_index<D>(hi, nsegfree, nb, r, cc);
-          if (i2 >= 0 && i3 >= 0) A[i2 * NS + i3] += v;
+          if (i2 >= 0 && i3 >= 0) A[i2 * lda + i3] += v;
         }
       }
     }
   }
+}
+
+// Build + invert.  One CTA (1024 threads) per instance that is in a line-search tick.
+template <int D, int TS>
+__device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, InstState *st, double reg, int every,
+                                                  const int inst) {
+  using CD = CoarseDims<D>;
+  constexpr int NP = 32 * TS;  // padded matrix dimension
+  constexpr int NS = NP + 1;   // shared-memory row stride (odd: transposed reads are bank-conflict free)
+  constexpr int NW = kCoarseThreads / 32;
+  extern __shared__ double sm[];
+  const int n = P.c_n[inst];
+  if (n <= 0 || n > NP || st[inst].phase != PH_LS || st[inst].eval_now) return;
+  // lagged coarse level: within one barrier stage the inverse is reused for `every` Newton steps
+  if (every > 1 && st[inst].mu == st[inst].mu_c && st[inst].c_age < every) {
+    __syncthreads();
+    if (threadIdx.x == 0) st[inst].c_age += 1;
+    return;
+  }
+  double *A = sm;                       // NP x NS
+  double *rowb = A + NP * NS;           // 2 x NP (NP * NS is even: 16-byte aligned)
+  double *pivb = rowb + 2 * NP;         // 2
+  double *stage = pivb + 2;             // NW x STAGE
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < NP * NS; i += kCoarseThreads) A[i] = 0.0;
+  __syncthreads();
+  const int nb = P.c_nb[inst];
+  double *mystage = stage + wid * CD::STAGE;
+
+  coarse_accumulate<D>(P, V, inst, reg, A, NS, wid, NW, true, mystage);
   __syncthreads();
   // landmark priors (w ||l - prior||^2) add 2 w on the diagonal
   if (tid == 0) {
@@ -427,6 +444,86 @@ __global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem
     coarse_apply_body<D>(P, V, st, act[ai]);
     __syncthreads();
   }
+}
+
+// ---- large coarse spaces (kCoarseMax < nc <= kCoarseBigMax, single-instance handles) -------------------------
+// Same sorted-list accumulation, but into a dense nc x nc matrix in global memory; the factorisation /
+// inversion is a plain library call (cuSOLVER potrf + potri, api.cu) and the application a dense mat-vec.
+
+constexpr int kBigThreads = 256;
+
+template <int D>
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_accum(DevProblem P, SolverVecs V, double reg, double *A) {
+  __shared__ double stage[(kBigThreads / 32) * CoarseDims<D>::STAGE];
+  const int wid = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (kBigThreads / 32) + wid, nw = gridDim.x * (kBigThreads / 32);
+  coarse_accumulate<D>(P, V, 0, reg, A, P.c_n[0], gw, nw, false, stage + wid * CoarseDims<D>::STAGE);
+}
+
+// priors on the landmark diagonals, identity for coordinates without curvature
+template <int D>
+__global__ void k_coarse_big_finish(DevProblem P, double *A) {
+  const int n = P.c_n[0], nb = P.c_nb[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = A[(size_t)i * n + i];
+  if (i >= nb) {
+    const int q = (i - nb) / D;
+    for (int pl = P.prior_off[0]; pl < P.prior_off[1]; ++pl)
+      if (P.prior_l[pl] == q) v += 2.0 * P.prior_w[pl];
+  }
+  if (!(v > 0.0)) v = 1.0;
+  A[(size_t)i * n + i] = v;
+}
+
+// potri leaves the inverse in one triangle (row-major upper = column-major lower): mirror it
+__global__ void k_mirror_upper(double *A, int n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * n) return;
+  const int i = (int)(t / n), j = (int)(t % n);
+  if (i > j) A[t] = A[(size_t)j * n + i];
+}
+
+// y = A_c^-1 c : one warp per row
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_apply(DevProblem P, const InstState *st) {
+  if (st[0].phase == PH_DONE || st[0].phase == PH_WAIT || st[0].eval_now) return;
+  const int n = P.c_n[0], lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (kBigThreads / 32) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const double *__restrict__ a = P.c_Ainv + (size_t)row * n;
+  const double *__restrict__ c = P.c_rhs;
+  double acc0 = 0.0, acc1 = 0.0;
+  int j = lane;
+  for (; j + 32 < n; j += 64) {
+    acc0 += __ldg(a + j) * c[j];
+    acc1 += __ldg(a + j + 32) * c[j + 32];
+  }
+  if (j < n) acc0 += __ldg(a + j) * c[j];
+  const double tot = warp_sum(acc0 + acc1);
+  if (lane == 0) P.c_sol[row] = tot;
+}
+
+// scatter: segment bases -> ytmp, landmarks -> s, partial r.s of the landmark block
+template <int D>
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_scatter(DevProblem P, SolverVecs V, const InstState *st) {
+  constexpr int BLK = D * (D + 1);
+  __shared__ double red[kBigThreads / 32];
+  if (st[0].phase == PH_DONE || st[0].phase == PH_WAIT || st[0].eval_now) return;
+  const int n = P.c_n[0], nb = P.c_nb[0];
+  const double *y = P.c_sol;
+  for (int i = threadIdx.x; i < nb; i += kBigThreads) {
+    const int pg = P.seg_ptr[1 + i / BLK];  // base pose of free segment i / BLK
+    V.ytmp[(size_t)pg * BLK + (i % BLK)] = y[i];
+  }
+  const int c0 = P.P * BLK;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < n - nb; j += kBigThreads) {
+    const double sv = y[nb + j];
+    V.s[c0 + j] = sv;
+    acc += sv * V.r[c0 + j];
+  }
+  const double tot = block_sum<kBigThreads>(acc, red);
+  if (threadIdx.x == 0) V.part_lm[0] = tot;
 }
 
 }  // namespace score

@@ -17,6 +17,7 @@ constexpr int kSegThreads = 128;  // chain-scan CTA width
 constexpr int kNumCand = 12;      // line-search candidates 2^(1 - c/2); slot kNumCand is a = 0
 constexpr int kCoarseMax = 128;   // largest per-instance coarse space handled by the dense on-chip solve (4 x 4 register tiles)
 constexpr int kCoarseThreads = 1024;
+constexpr int kCoarseBigMax = 8192;  // largest coarse space of the dense global-memory path (single-instance handles)
 constexpr int kLsSums = kNumCand + 1 + 3;
 
 // Per-instance phase.  PH_WAIT: this Newton system is solved to its forcing tolerance; idle until the
@@ -80,6 +81,7 @@ struct DevProblem {
   int *c_pr_off, *c_pr_code;         // [n_inst+1] ; [c_npair] (local range << 1) | (1: endpoint b is the lower slot)
   double *c_pr_h;                    // [c_npair x 2 (d+1)] frames of the lower / higher slot endpoint
   int *c_orun_lo, *c_orun_hi, *c_orun_begin;     // off-diagonal runs: [n_orun] x2 ; [n_orun+1]
+  int *c_orun_off;                   // [n_inst+1] first off-diagonal run of every instance
   int *c_owarp;                      // [n_inst x 33] first off-diagonal run of every warp of the build CTA
   int *c_off, *c_moff, *c_n, *c_nb;  // [n_inst(+1)]
   double *c_Ainv;                 // per instance nc x nc inverse coarse Hessian
@@ -96,6 +98,8 @@ struct SolverVecs {
   double *part_row;  // [n_row_blocks] pHp
   double *part_ls;   // [n_row_blocks * kLsSums]
   double *part_upd;  // [n_row_blocks * 2]  F, |delta|^2
+  double *hloc;      // [nz] B^T u of this rank's rows (row-partitioned solve: SpMV and update are separate passes)
+  const double *hglob;  // [nz] its sum over the ranks
   double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2
   double *part_seg;  // [n_seg] r.s over chain segments
   double *part_lm;   // [n_inst] r.s over landmarks
@@ -124,6 +128,7 @@ struct WorkLists {
   int *ev;      //  kernel-parameter arrays, which would force a local-memory copy of the parameters)
   int n_inst;
   int maxrb, maxcb, maxseg;  // most row blocks / column blocks / chain segments any instance has
+  int rb_lo, rb_hi;          // row blocks this rank owns (row-partitioned multi-GPU solve; [0, n_rb) otherwise)
   __device__ __forceinline__ int *list(int parity, int kind) const { return lists + (size_t)(parity * 3 + kind) * n_inst; }
 };
 __device__ __forceinline__ void wl_get(const WorkLists &W, int kind, const int *&list, int &n) {

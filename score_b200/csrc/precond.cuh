@@ -77,8 +77,15 @@ __global__ void k_diag_setup(DevProblem P, double *wsum) {
     const int col = P.zoff[inst] + Pi * blk + (lq - P.lm_off[inst]) * d + r;
     double acc = 0.0;
     for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) acc += P.w[P.t_rows[k]] * P.t_vals[k] * P.t_vals[k];
-    P.lm_inv[j] = (acc > 0.0) ? 1.0 / (2.0 * acc) : 1.0;
+    P.lm_inv[j] = acc;  // raw sum; k_lm_finish inverts it (after the sum over ranks in a row-partitioned solve)
   }
+}
+
+__global__ void k_lm_finish(DevProblem P) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P.L * P.d) return;
+  const double acc = P.lm_inv[j];
+  P.lm_inv[j] = (acc > 0.0) ? 1.0 / (2.0 * acc) : 1.0;
 }
 
 // In-place inverse of a small SPD matrix (n <= 4) by Gauss-Jordan.

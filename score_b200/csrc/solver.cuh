@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
   wl_get(W, WL_RUN, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
     const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
-    if (bid < T.rb_begin[inst + 1]) rowpass_body<D>(P, V, T, st, bid);
+    if (bid < T.rb_begin[inst + 1] && bid >= W.rb_lo && bid < W.rb_hi) rowpass_body<D>(P, V, T, st, bid);
   }
 }
 
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVec
   wl_get(W, WL_LS, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
     const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
-    if (bid < T.rb_begin[inst + 1]) linesearch_body<D>(P, V, T, st, bid);
+    if (bid < T.rb_begin[inst + 1] && bid >= W.rb_lo && bid < W.rb_hi) linesearch_body<D>(P, V, T, st, bid);
   }
 }
 
@@ -417,14 +417,17 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
   wl_get(W, mode == TM_EVAL ? WL_EVAL : WL_LS, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
     const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
-    if (bid < T.rb_begin[inst + 1]) rowupdate_body<D>(P, V, T, st, mode, bid);
+    if (bid < T.rb_begin[inst + 1] && bid >= W.rb_lo && bid < W.rb_hi) rowupdate_body<D>(P, V, T, st, mode, bid);
   }
 }
 
 // ---- K2: h = B^T u.  PH_CG: dz += alpha p, r -= alpha h.  PH_LS: z += step dz, dz = 0, r = -h (h is the
 // gradient of F_mu at the new point).  Evaluation ticks: partial |g|^2, g.z, |z|^2 of the true gradient only.
+// `split` (row-partitioned multi-GPU solve): 0 fused; 1 SpMV only (h of this rank's rows -> V.hloc); 2 update only
+// (h read from V.hglob, the sum over the ranks).
+enum ColSplit : int { CS_FUSED = 0, CS_SPMV = 1, CS_APPLY = 2 };
 __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
-                                                      int mode, const int bid) {
+                                                      int mode, int split, const int bid) {
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.cb[bid];
   const int inst = bd.inst;
@@ -436,6 +439,10 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
   const int pin_end = P.zoff[inst] + P.blk;
   double gg = 0.0, gz = 0.0, zz = 0.0;
   auto apply = [&](int col, double h) {
+    if (split == CS_SPMV) {
+      V.hloc[col] = h;
+      return;
+    }
     if (col < pin_end) h = 0.0;
     if (eval) {
       const double zc = V.z[col];
@@ -456,7 +463,11 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
     for (int lc = threadIdx.x; lc < ncols; lc += kThreads) {
       const int col = bd.i0 + lc;
       double h = 0.0;
-      for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
+      if (split == CS_APPLY) {
+        h = V.hglob[col];
+      } else {
+        for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
+      }
       apply(col, h);
     }
   } else {
@@ -465,13 +476,17 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
     for (int lc = wid; lc < ncols; lc += kThreads / 32) {
       const int col = bd.i0 + lc;
       double h = 0.0;
-      for (int k = P.t_indptr[col] + lane; k < P.t_indptr[col + 1]; k += 32)
-        h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
-      h = warp_sum(h);
+      if (split == CS_APPLY) {
+        h = V.hglob[col];
+      } else {
+        for (int k = P.t_indptr[col] + lane; k < P.t_indptr[col + 1]; k += 32)
+          h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
+        h = warp_sum(h);
+      }
       if (lane == 0) apply(col, h);
     }
   }
-  if (eval) {
+  if (eval && split != CS_SPMV) {
     const double a = block_sum<kThreads>(gg, red);
     const double b = block_sum<kThreads>(gz, red);
     const double c = block_sum<kThreads>(zz, red);
@@ -484,13 +499,13 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
 }
 
 __global__ void __launch_bounds__(kThreads) k_colpass(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
-                                                      int mode, WorkLists W) {
+                                                      int mode, int split, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, mode == TM_EVAL ? WL_EVAL : WL_RUN, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxcb; item += gridDim.x) {
     const int inst = act[item / W.maxcb], bid = T.cb_begin[inst] + (int)(item % W.maxcb);
-    if (bid < T.cb_begin[inst + 1]) colpass_body(P, V, T, st, mode, bid);
+    if (bid < T.cb_begin[inst + 1]) colpass_body(P, V, T, st, mode, split, bid);
   }
 }
 

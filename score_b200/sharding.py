@@ -117,3 +117,42 @@ def solve_score_sharded(datas, relaxation_type: str = "QCQP", device: Optional[i
         if len(local) != len(mine):
             raise RuntimeError("solve_fn returned a different number of results than instances")
     return gather_results(mine, local, len(datas), group=group, dst=dst)
+
+
+def row_block_range(n_blocks: int, rank: int, world_size: int) -> range:
+    """Row blocks (of 768 measurement rows) rank ``rank`` owns in a row-partitioned solve — the same split
+    ``score_comm_init`` computes on the device side (api.cu)."""
+    return range(rank * n_blocks // world_size, (rank + 1) * n_blocks // world_size)
+
+
+def solve_row_partitioned(prob, device: Optional[int] = None, group=None, **solver_kw):
+    """Solve ONE large lowered instance with its measurement rows partitioned over the ranks of a
+    ``torch.distributed`` group (BASELINE configs[4]).
+
+    Every rank passes the same ``prob``; the column-space vectors are replicated, each rank applies B and B^T
+    for its own rows and one NCCL all-reduce per iteration sums the B^T u partials together with the scalar
+    partial sums.  Returns ``(stats, (poses, rounded, landmarks, dist))`` on every rank (identical bits).
+    """
+    import torch
+    import torch.distributed as dist
+
+    from .solver import ScoreSolver
+
+    if prob.n_instances != 1:
+        raise ValueError("row partitioning applies to a single instance; shard batches with solve_score_sharded")
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    if device is None:
+        device = rank % max(1, torch.cuda.device_count())
+    solver = ScoreSolver(prob, device=device)
+    try:
+        if world > 1:
+            box = [ScoreSolver.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            solver.comm_init(world, rank, box[0])
+        stats = solver.solve(**solver_kw)
+        return stats, solver.solution()
+    finally:
+        solver.close()

@@ -115,6 +115,21 @@ class ScoreSolver:
     def __exit__(self, *exc):
         self.close()
 
+    # -- row-partitioned multi-GPU solve of one large instance -------------------------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """128-byte NCCL id (call on rank 0, ship to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        _check(_lib.load().score_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        """Join the communicator: from now on ``solve()`` splits the measurement rows over the ranks and
+        all-reduces the B^T u partials once per iteration (score_comm_init)."""
+        if len(unique_id) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        _check(self._lib.score_comm_init(self._h, n_ranks, rank, unique_id))
+
     # -- solve -----------------------------------------------------------------------------
     def solve(
         self,
