@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU-baseline step (0: one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--first-instance", type=int, default=0, help="sweep index of rank 0's first instance")
     ap.add_argument("--streams", type=int, default=2, help="sub-batches per GPU solved concurrently on their own streams")
     return ap.parse_args()
 
@@ -289,7 +290,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     from score_b200.solver import KERNEL_NAMES, ScoreSolver, ScoreSolverGroup
 
     # generate the shard before CUDA is initialised (the generator forks worker processes)
-    prob = make_batch(rank * args.instances, args.instances, args.robots, args.poses)
+    prob = make_batch(args.first_instance + rank * args.instances, args.instances, args.robots, args.poses)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -328,7 +329,12 @@ def run_gpu_arm(args, rank, local_rank, world):
     barrier()
     clocks = sampler.stop()
     t_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    per_rank = [[float(t_ms.item()) / args.steps, cycles / args.steps]]
     if world > 1:
+        mine = torch.tensor(per_rank[0], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[float(v) for v in t.tolist()] for t in allr]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         agg = torch.tensor([float(n_solved), float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
@@ -458,6 +464,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "instances": total_instances,
             "ticks_per_step": ticks / args.steps,
             "cycles_per_step": cycles / args.steps,
+            "per_rank_ms_and_cycles_per_step": per_rank,
             "impl": "score_b200",
         }
         print(json.dumps(line), flush=True)

@@ -97,7 +97,7 @@ typedef struct {
   int32_t max_cg;          /* inner PCG iteration cap per Newton step, <=0: default  */
   int32_t max_ticks;       /* global cap on solver ticks, <=0: default               */
   double kkt_tol;          /* relative KKT tolerance, <=0: 1e-6    */
-  double cg_forcing;       /* inexact-Newton forcing term eta, <=0: 0.1              */
+  double cg_forcing;       /* inexact-Newton forcing term eta, <=0: 0.2 (x0.3 on the last barrier stages) */
   int32_t cg_per_cycle;    /* PCG ticks between two line-search ticks of the batch, <=0: default 4 */
   int32_t verbose;
   void *stream;            /* cudaStream_t to run on, NULL: library-owned stream     */

@@ -604,7 +604,12 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     h->cb_begin[i] = (int)cb.size();
     const int pc0 = h->zoff[i], pc1 = pc0 + (h->pose_off[i + 1] - h->pose_off[i]) * (int)blk;
     for (int c0 = pc0; c0 < pc1; c0 += kColsPerBlock) cb.push_back({i, c0, std::min(c0 + kColsPerBlock, pc1), CB_POSE});
-    for (int c0 = pc1; c0 < h->zoff[i + 1]; c0 += 64) cb.push_back({i, c0, std::min(c0 + 64, h->zoff[i + 1]), CB_LANDMARK});
+    // landmark columns are processed one warp per column: heavy columns (many ranges per landmark) get one
+    // column per warp and CTA-sized blocks of 8 so that they spread over the SMs
+    const int Li = h->lm_off[i + 1] - h->lm_off[i], Ki = h->rng_off[i + 1] - h->rng_off[i];
+    const int lstep = (Li > 0 && Ki / Li > 128) ? kThreads / 32 : 64;
+    for (int c0 = pc1; c0 < h->zoff[i + 1]; c0 += lstep)
+      cb.push_back({i, c0, std::min(c0 + lstep, h->zoff[i + 1]), CB_LANDMARK});
   }
   h->rb_begin[NI] = (int)rb.size();
   h->cb_begin[NI] = (int)cb.size();
@@ -955,7 +960,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   if (params && prm.max_newton == -1) cfg.max_newton = 0;  // "evaluate the start point only"
   cfg.max_cg = prm.max_cg > 0 ? prm.max_cg : 100;
   cfg.kkt_tol = prm.kkt_tol > 0 ? prm.kkt_tol : 1e-6;
-  cfg.forcing = prm.cg_forcing > 0 ? prm.cg_forcing : 0.1;
+  cfg.forcing = prm.cg_forcing > 0 ? prm.cg_forcing : 0.2;
   cfg.mu0 = prm.mu0 > 0 ? prm.mu0 : (prm.mu0 < 0 ? 0.0 : 1.0);
   cfg.mu_factor = (prm.mu_factor > 0 && prm.mu_factor < 1) ? prm.mu_factor : 0.1;
   cfg.center_tol = prm.center_tol > 0 ? prm.center_tol : 4.0;

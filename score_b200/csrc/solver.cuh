@@ -84,7 +84,8 @@ __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, do
   return t;
 }
 
-// Value only (line search): phi_mu(n).
+// Value only (line search): phi_mu(n).  (Warm-starting the root search from a neighbouring step size was tried
+// and rejected: the stationarity cubic has other real roots and Newton then occasionally lands on one of them.)
 __device__ __forceinline__ double range_value(double n, double r, double w, double mu) {
   if (!(r > 0.0)) return w * n * n;
   if (mu == 0.0) {
@@ -583,7 +584,9 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
   S.cg_it = 0;
   S.end_cg = 0;
   S.dec = 0.0;
-  S.eta = cfg.forcing;
+  // inexact-Newton forcing term: tighter on the last barrier stages (the certificate needs the accuracy) and right
+  // after a line search that found no decrease (the direction was too inexact to be a descent direction)
+  S.eta = cfg.forcing * ((S.mu <= cfg.mu_eval) ? 0.3 : 1.0) * ((S.step == 0.0 && S.newton_it > 0) ? 0.1 : 1.0);
   if (S.want_eval || !(rs_new > 0.0) || S.newton_it >= cfg.max_newton || !isfinite(Fmu)) S.eval_now = 1;
   S.want_eval = 0;
 }

@@ -54,6 +54,11 @@ with ScoreSolver(prob, device=local_rank) as s:
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(f"ranks agree bitwise: {bool((lo == hi).all().item())}  world={world}", flush=True)
+    if rank == 0 and kw.get("profile_cycles"):
+        from score_b200.solver import KERNEL_NAMES
+        tot = st.kernel_ms.sum()
+        for k, ms, c in zip(KERNEL_NAMES, st.kernel_ms, st.kernel_count):
+            print(f"  {k:16s} {ms:9.1f} ms {100 * ms / max(tot, 1e-9):5.1f}%  launches {int(c):6d}  avg {1e3 * ms / max(1, c):8.1f} us")
     if rank == 0:
       print(f"solved={rec['solved']} kkt={rec['rel_kkt']:.3e} f={rec['objective']:.6f} newton={rec['newton_iters']} "
           f"cg={rec['cg_iters']} lsfail={rec['ls_failures']} ticks={st.ticks} cycles={st.cycles} "

@@ -12,7 +12,8 @@ import numpy as np
 import bench
 
 n = int(sys.argv[1])
-prob = bench.make_batch(0, n, 20, 100)
+first = int(os.environ.get("FIRST", "0"))
+prob = bench.make_batch(first, n, 20, 100)
 from score_b200 import build
 
 build.build()
@@ -32,3 +33,6 @@ with ScoreSolver(prob) as s:
               f"newton p50/p99/max {np.percentile(I['newton_iters'], 50):.0f}/{np.percentile(I['newton_iters'], 99):.0f}/{I['newton_iters'].max()} "
               f"cg mean {I['cg_iters'].mean():.1f} max {I['cg_iters'].max()} lsfail {int((I['ls_failures'] > 0).sum())} "
               f"maxkkt {I['rel_kkt'].max():.2e}", flush=True)
+        worst = np.argsort(-(I["newton_iters"] + 1000 * (1 - I["solved"])))[:6]
+        for w in worst:
+            print("    inst", first + int(w), {k: (float(I[w][k]) if I[w][k].dtype.kind == "f" else int(I[w][k])) for k in I.dtype.names}, flush=True)

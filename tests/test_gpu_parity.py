@@ -326,3 +326,18 @@ def test_stream_group_matches_single_handle_bitwise(built_lib, golden):
     assert np.array_equal(stg.instances["cg_iters"], st.instances["cg_iters"])
     for a, b, c in zip(ref, got, piped):
         assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_intermediate_iterates(built_lib, golden):
+    """solve_problem_with_intermediate_iterates (solve_score.py:89-116): one SolverResults per outer-iteration cap;
+    the objective decreases towards the optimum and the last entry is the converged solve."""
+    from score.solve_score import solve_problem_with_intermediate_iterates
+
+    fg, extra = golden("mc0_small")
+    its = solve_problem_with_intermediate_iterates(fg, "QCQP", max_iterates=60)
+    assert 3 <= len(its) <= 60
+    assert its[-1].solved and not its[0].solved
+    costs = [r.solver_cost for r in its]
+    assert costs[-1] <= costs[0] + 1e-12
+    names = [p.name for c in fg.pose_variables for p in c]
+    assert all(list(r.variables.poses.keys()) == names for r in its)
