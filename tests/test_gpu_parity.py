@@ -341,3 +341,83 @@ def test_intermediate_iterates(built_lib, golden):
     assert costs[-1] <= costs[0] + 1e-12
     names = [p.name for c in fg.pose_variables for p in c]
     assert all(list(r.variables.poses.keys()) == names for r in its)
+
+
+def _edge_case_graph(kind):
+    """Small 2D graphs exercising the rarely-hit branches of the reference model build."""
+    import score_b200  # noqa: F401
+    from py_factor_graph.factor_graph import FactorGraphData
+    from py_factor_graph.measurements import FGRangeMeasurement, PoseMeasurement2D
+    from py_factor_graph.priors import LandmarkPrior2D
+    from py_factor_graph.variables import LandmarkVariable2D, PoseVariable2D
+
+    rng = np.random.default_rng(42)
+    fg = FactorGraphData(2)
+    n = 30
+    th = np.cumsum(rng.normal(0, 0.3, n))
+    pos = np.cumsum(np.stack([np.cos(th), np.sin(th)], 1), 0)
+    for i in range(n):
+        fg.add_pose_variable(PoseVariable2D(f"A{i}", tuple(pos[i]), float(th[i]), float(i)), chain=0)
+    for q, p in enumerate([(3.0, 8.0), (12.0, -4.0), (20.0, 6.0)]):
+        fg.add_landmark_variable(LandmarkVariable2D(f"L{q}", p))
+
+    def rel(i, j, noise=0.02):
+        c, s = np.cos(th[i]), np.sin(th[i])
+        d = pos[j] - pos[i]
+        return PoseMeasurement2D(f"A{i}", f"A{j}", c * d[0] + s * d[1] + rng.normal(0, noise),
+                                 -s * d[0] + c * d[1] + rng.normal(0, noise), th[j] - th[i] + rng.normal(0, 0.01),
+                                 1.0 / noise**2, 1e4, float(i))
+
+    skip = {14} if kind == "broken_chain" else set()
+    for i in range(n - 1):
+        if i not in skip:
+            fg.add_odom_measurement(0, rel(i, i + 1))
+    if kind in ("loop_closures", "broken_chain"):
+        for i, j in [(2, 20), (5, 27), (10, 16)]:
+            fg.add_loop_closure(rel(i, j, 0.05))
+    if kind != "no_ranges":
+        lms = np.array([l.true_position for l in fg.landmark_variables])
+        for i in range(0, n, 2):
+            for q in range(3):
+                dist = np.linalg.norm(pos[i] - lms[q]) + rng.normal(0, 0.5)
+                fg.add_range_measurement(FGRangeMeasurement((f"A{i}", f"L{q}"), max(dist, 0.0), 0.5, float(i)))
+        fg.add_range_measurement(FGRangeMeasurement(("L0", "L1"), 0.0, 1.0, 0.0))  # dist == 0: all-zero delta column
+    else:
+        fg.landmark_variables.clear()
+        fg.existing_landmark_variables.clear() if hasattr(fg, "existing_landmark_variables") else None
+    if kind == "priors":
+        fg.add_landmark_prior(LandmarkPrior2D("L0", (3.5, 7.5), 4.0))
+        fg.add_landmark_prior(LandmarkPrior2D("L2", (19.0, 6.5), 0.25))
+    assert len(fg.unconnected_variable_names) == 0
+    return fg
+
+
+@pytest.mark.parametrize("kind", ["priors", "loop_closures", "broken_chain", "no_ranges"])
+@pytest.mark.parametrize("relax", ["QCQP", "SOCP"])
+def test_edge_case_graphs_match_oracle(built_lib, kind, relax):
+    """Landmark priors (get_all_landmark_prior_costs :433-446), loop closures (:407-430), an odometry chain with a
+    missing link, a range with dist == 0, and a graph without ranges (add_distance_variables early return :281-283):
+    assembly bit-exact, optimum equal to the oracle's."""
+    from oracle import score_oracle as so
+    from score_b200 import _lib
+
+    fg = _edge_case_graph(kind)
+    prob = so.assemble(fg, relax)
+    with _solver(fg, relax) as s:
+        indptr, indices, values, w, b, shape = s.csr(_lib.SCORE_CSR_FULL, 0)
+        st = s.solve()
+        poses, rounded, lms, dist = s.solution()
+    assert shape == prob.B.shape
+    assert np.array_equal(indptr, prob.B.indptr) and np.array_equal(indices, prob.B.indices)
+    assert np.array_equal(values, prob.B.data) and np.array_equal(w, prob.w) and np.array_equal(b, prob.b)
+    rec = st.instances[0]
+    assert rec["solved"] == 1
+    pq, xq, _ = so.solve(fg, so.QCQP)
+    f_star = so.objective(pq, xq)
+    assert abs(rec["objective"] - f_star) <= 1e-6 * max(1.0, abs(f_star))
+    x = _full_x(prob, poses, lms, dist)
+    assert abs(so.objective(prob, x) - rec["objective"]) <= 1e-9 * max(1.0, abs(f_star))
+    if relax == "QCQP":
+        assert so.kkt_qcqp(prob, x)["rel_kkt"] <= 1e-6
+    nz = pq.P * 6
+    assert np.abs(poses.ravel() - xq[:nz]).max() <= 1e-3  # single pinned chain: unique optimum
