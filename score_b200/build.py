@@ -26,17 +26,32 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libscore_b200.so if it is missing or older than its sources.  Safe to call from several processes
+    at once (one rank per GPU): an exclusive file lock serialises them and the output is renamed into place."""
+    import fcntl
+
     if not force and not _stale():
         return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES]
-           + ["-o", OUT, "-lcusolver", "-lcublas", "-ldl"])
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libscore_b200.so")
-    if verbose:
-        print(res.stderr)
+    with open(OUT + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():  # another process built it while we waited
+                return OUT
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = OUT + f".tmp{os.getpid()}"
+            cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+                   + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp, "-lcusolver", "-lcublas", "-ldl"])
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libscore_b200.so")
+            os.replace(tmp, OUT)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 

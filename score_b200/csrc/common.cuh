@@ -39,7 +39,7 @@ struct InstState {
   int newton_it, cg_it, total_cg, ls_fail;
   int eval_now, want_eval, n_eval, stall;  // true-KKT evaluation ticks
   double alpha, beta, rs, rs0, eta, step;
-  int c_age, pad0;                         // Newton steps the current coarse inverse has served
+  int c_age, ls_shift;                     // Newton steps the current coarse inverse has served; line-search ladder shift
   double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;

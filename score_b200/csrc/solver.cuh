@@ -26,9 +26,12 @@
 namespace score {
 
 __device__ __forceinline__ double ls_candidate(int c) {
-  // 2^(1 - c/2), c = 0..kNumCand-1
+  // 2^(1 - c/2), c = 0..kNumCand-1 (compile-time constants in the unrolled loops)
   return ldexp((c & 1) ? 1.4142135623730951 : 1.0, 1 - (c + 1) / 2);
 }
+// After a line search without any decrease the same direction is tried again on a ladder of 64x shorter steps
+// (shift 1), then 4096x (shift 2), ...
+__device__ __forceinline__ double ls_scale(int shift) { return ldexp(1.0, -6 * shift); }
 
 // eps = 1 - rho*, the root in (0,1] of (q - 1 + e) e (2 - e) = kap (1 - e)   (stationarity of phi_mu in rho
 // with q = n / r, kap = mu / (w r^2)); parametrised by eps so that rho -> 1 keeps full relative accuracy.
@@ -202,6 +205,7 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
   const int inst = bd.inst;
   if (st[inst].phase != PH_LS || st[inst].skip_ls || st[inst].eval_now) return;
   const double mu = st[inst].mu;
+  const double lsc = ls_scale(st[inst].ls_shift);
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
   double sums[kLsSums];
@@ -233,9 +237,11 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
         Bq += v * qq;
         C += qq * qq;
       }
+      Bq *= lsc;
+      C *= lsc * lsc;
 #pragma unroll
       for (int c = 0; c < kNumCand; ++c) {
-        const double a = ls_candidate(c);
+        const double a = ls_candidate(c);  // compile-time constant; the ladder scale is folded into Bq, C
         const double n = sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C)));
         sums[3 + c] += range_value(n, rr, wk, mu);
       }
@@ -301,7 +307,7 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
   if (lane == 0) {
     double best = tot[0] + tot[3 + kNumCand], step = 0.0;
     for (int c = 0; c < kNumCand; ++c) {
-      const double a = ls_candidate(c);
+      const double a = ls_candidate(c) * ls_scale(S.ls_shift);
       const double Fc = tot[0] + a * (2.0 * tot[1] + a * tot[2]) + tot[3 + c];
       if (Fc < best) {
         best = Fc;
@@ -314,7 +320,11 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
     // candidate improved — the barrier parameter shrinks; the gradient of this tick already uses it
     const double lam2 = (S.mu > 0.0) ? S.dec / S.mu : 0.0;
     S.want_eval = 0;
-    if (S.mu > 0.0 && (lam2 <= cfg.center_tol || step == 0.0)) {
+    // no decrease although the iterate is not centred: the Newton step is too long for the ladder -> solve the same
+    // system again (tighter forcing term, ctrl_b) and search 64x shorter steps; give up on the stage after 3 shifts
+    const bool retry = step == 0.0 && lam2 > cfg.center_tol && S.ls_shift < 3;
+    S.ls_shift = retry ? S.ls_shift + 1 : 0;
+    if (S.mu > 0.0 && !retry && (lam2 <= cfg.center_tol || step == 0.0)) {
       if (S.mu <= cfg.mu_eval) S.want_eval = 1;
       if (S.mu <= cfg.mu_min) S.stall += 1;
       S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
