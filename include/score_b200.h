@@ -190,6 +190,25 @@ int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, double *out, 
  * round_to_special_orthogonal, score/utils/matrix_utils.py:59-79. */
 int score_round_so(int32_t dim, int64_t n, const double *mats, double *out, int32_t device);
 
+/* Evaluation step after the path (the reference ships ground truth beside its inputs —
+ * PoseVariable.true_position in examples/manhattan/factor_graph.pickle, examples/goats_14_data/gt_traj_A.tum — and
+ * leaves the trajectory-error computation to downstream tooling): absolute trajectory error of n_traj
+ * trajectories after the best rigid alignment  min_{R in SO(d), t} sum ||gt_i - (R est_i + t)||^2  (Kabsch; the
+ * rotation is the same U diag(1,..,det) V^T rule as round_to_special_orthogonal, matrix_utils.py:59-79).
+ *   traj_off [n_traj+1]  point offsets of the trajectories (non-decreasing)
+ *   est, gt  [n*dim]     estimated / true positions, row-major (host pointers)
+ *   align                1: SE(d) alignment, 0: compare as is (R = I, t = 0)
+ *   rmse [n_traj], R [n_traj*dim*dim], t [n_traj*dim]   outputs, any may be NULL; an empty trajectory gives NaN
+ * One CTA per trajectory, fixed-order reductions (bit-reproducible). */
+int score_trajectory_ate(int32_t dim, int32_t n_traj, const int32_t *traj_off, const double *est, const double *gt,
+                         int32_t align, double *rmse, double *R, double *t, int32_t device);
+
+/* Same, on the translations of the solution held by a solved handle (no device-to-host copy of the estimate).
+ * traj_off: [n_traj+1] offsets into the batch's global pose numbering (e.g. one trajectory per robot chain);
+ * NULL = one trajectory per instance (n_traj is then ignored).  gt_pos: [P*dim] host. */
+int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj_off, const double *gt_pos, int32_t align,
+                   double *rmse, double *R, double *t);
+
 void score_destroy(ScoreHandle h);
 const char *score_last_error(void);
 const char *score_version(void);

@@ -479,6 +479,28 @@ def round_rotations(poses: np.ndarray) -> np.ndarray:
     return out
 
 
+def align_trajectory(est: np.ndarray, gt: np.ndarray, align: bool = True):
+    """Checker for the evaluation step: the rigid alignment
+    min_{R in SO(d), t} sum ||gt_i - (R est_i + t)||^2 by the Kabsch SVD — the same U diag(1,..,det) Vh rule as
+    round_to_special_orthogonal (score/utils/matrix_utils.py:59-79) applied to the cross-covariance — and the
+    absolute trajectory error after it.  Returns (rmse, R, t); an empty trajectory gives (nan, I, 0)."""
+    est, gt = np.asarray(est, float), np.asarray(gt, float)
+    n, d = est.shape
+    if n == 0:
+        return float("nan"), np.eye(d), np.zeros(d)
+    if not align:
+        return float(np.sqrt(((gt - est) ** 2).sum() / n)), np.eye(d), np.zeros(d)
+    me, mg = est.mean(0), gt.mean(0)
+    H = (gt - mg).T @ (est - me)
+    U, _, Vh = np.linalg.svd(H)
+    R = U @ Vh
+    if np.linalg.det(R) < 0:
+        R = U @ np.diag([1.0] * (d - 1) + [-1.0]) @ Vh
+    t = mg - R @ me
+    res = gt - (est @ R.T + t)
+    return float(np.sqrt((res ** 2).sum() / n)), R, t
+
+
 def extract(prob: OracleProblem, x: np.ndarray):
     """VariableCollection.get_variable_values (score/utils/gurobi_utils.py:114-136):
     homogeneous (d+1)x(d+1) poses with rounded rotation and untouched translation."""

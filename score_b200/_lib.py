@@ -128,6 +128,8 @@ EXPORTED_SYMBOLS = [
     "score_comm_init",
     "score_get_internal",
     "score_round_so",
+    "score_trajectory_ate",
+    "score_eval_ate",
     "score_destroy",
     "score_last_error",
     "score_version",
@@ -181,6 +183,12 @@ def load() -> C.CDLL:
     lib.score_get_internal.restype = C.c_int
     lib.score_round_so.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     lib.score_round_so.restype = C.c_int
+    lib.score_trajectory_ate.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.score_trajectory_ate.restype = C.c_int
+    lib.score_eval_ate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
+    lib.score_eval_ate.restype = C.c_int
     lib.score_destroy.argtypes = [C.c_void_p]
     lib.score_destroy.restype = None
     lib.score_last_error.restype = C.c_char_p

@@ -15,6 +15,7 @@
 #include "assemble.cuh"
 #include "coarse.cuh"
 #include "common.cuh"
+#include "evaluate.cuh"
 #include "extract.cuh"
 #include "precond.cuh"
 #include "solver.cuh"
@@ -200,6 +201,111 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
 
 extern "C" const char *score_last_error(void) { return g_score_last_error.c_str(); }
 extern "C" const char *score_version(void) { return "score_b200 0.1.0 (sm_100a)"; }
+
+// ---- evaluation after the path: SE(d)-aligned absolute trajectory error, batched (evaluate.cuh) --------------
+namespace {
+// est / gt / off are device pointers; outputs are host pointers (any may be null)
+int ate_launch(int dim, int n_traj, const int *d_off, const double *d_est, long es, int ecs, int ec0, const double *d_gt,
+               int align, double *rmse, double *R, double *t, cudaStream_t st) {
+  double *d_out = nullptr;
+  const size_t per = 1 + (size_t)dim * dim + dim;
+  SCORE_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * per * n_traj));
+  double *d_rmse = d_out, *d_R = d_out + n_traj, *d_t = d_R + (size_t)n_traj * dim * dim;
+  const int grid = std::min(n_traj, 148 * 8);
+  if (dim == 2)
+    k_ate<2><<<grid, kAteThreads, 0, st>>>(n_traj, d_off, d_est, es, ecs, ec0, d_gt, align, d_rmse, d_R, d_t);
+  else
+    k_ate<3><<<grid, kAteThreads, 0, st>>>(n_traj, d_off, d_est, es, ecs, ec0, d_gt, align, d_rmse, d_R, d_t);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && rmse) e = cudaMemcpy(rmse, d_rmse, sizeof(double) * n_traj, cudaMemcpyDefault);
+  if (e == cudaSuccess && R) e = cudaMemcpy(R, d_R, sizeof(double) * (size_t)n_traj * dim * dim, cudaMemcpyDefault);
+  if (e == cudaSuccess && t) e = cudaMemcpy(t, d_t, sizeof(double) * (size_t)n_traj * dim, cudaMemcpyDefault);
+  cudaFree(d_out);
+  SCORE_CUDA_CHECK(e);
+  return SCORE_OK;
+}
+int ate_check_offsets(int n_traj, const int32_t *off, int64_t n_points) {
+  if (n_traj < 0 || (n_traj > 0 && !off)) {
+    g_score_last_error = "null trajectory offsets";
+    return SCORE_ERR_INVALID;
+  }
+  for (int i = 0; i < n_traj; ++i)
+    if (off[i] < 0 || off[i + 1] < off[i] || (n_points >= 0 && off[i + 1] > n_points)) {
+      g_score_last_error = "trajectory offsets must be non-decreasing and within the point array";
+      return SCORE_ERR_INVALID;
+    }
+  return SCORE_OK;
+}
+}  // namespace
+
+extern "C" int score_trajectory_ate(int32_t dim, int32_t n_traj, const int32_t *traj_off, const double *est,
+                                    const double *gt, int32_t align, double *rmse, double *R, double *t, int32_t device) {
+  if (dim != 2 && dim != 3) {
+    g_score_last_error = "Value " + std::to_string(dim) + " is not 2 or 3";
+    return SCORE_ERR_INVALID;
+  }
+  int rc = ate_check_offsets(n_traj, traj_off, -1);
+  if (rc) return rc;
+  if (n_traj == 0) return SCORE_OK;
+  const size_t n = (size_t)traj_off[n_traj];
+  if (n > 0 && (!est || !gt)) {
+    g_score_last_error = "null argument";
+    return SCORE_ERR_INVALID;
+  }
+  SCORE_CUDA_CHECK(cudaSetDevice(device));
+  int *d_off = nullptr;
+  double *d_pts = nullptr;  // [est | gt]
+  SCORE_CUDA_CHECK(cudaMalloc(&d_off, sizeof(int) * (n_traj + 1)));
+  cudaError_t e = cudaMalloc(&d_pts, sizeof(double) * std::max<size_t>(1, 2 * n * dim));
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, traj_off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
+  if (e == cudaSuccess && n) e = cudaMemcpy(d_pts, est, sizeof(double) * n * dim, cudaMemcpyDefault);
+  if (e == cudaSuccess && n) e = cudaMemcpy(d_pts + n * dim, gt, sizeof(double) * n * dim, cudaMemcpyDefault);
+  rc = SCORE_OK;
+  if (e == cudaSuccess)
+    rc = ate_launch(dim, n_traj, d_off, d_pts, dim, 1, 0, d_pts + n * dim, align, rmse, R, t, nullptr);
+  cudaFree(d_off);
+  cudaFree(d_pts);
+  SCORE_CUDA_CHECK(e);
+  return rc;
+}
+
+extern "C" int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj_off, const double *gt_pos, int32_t align,
+                              double *rmse, double *R, double *t) {
+  if (!h) {
+    g_score_last_error = "null handle";
+    return SCORE_ERR_INVALID;
+  }
+  if (!h->solved_once) {
+    g_score_last_error = "score_eval_ate called before score_solve";
+    return SCORE_ERR_STATE;
+  }
+  const DevProblem &P = h->P;
+  // default: one trajectory per instance
+  const int32_t *off = traj_off ? traj_off : h->pose_off.data();
+  if (!traj_off) n_traj = P.n_inst;
+  int rc = ate_check_offsets(n_traj, off, P.P);
+  if (rc) return rc;
+  if (n_traj == 0) return SCORE_OK;
+  if (!gt_pos) {
+    g_score_last_error = "null ground truth";
+    return SCORE_ERR_INVALID;
+  }
+  SCORE_CUDA_CHECK(cudaSetDevice(h->device));
+  int *d_off = nullptr;
+  double *d_gt = nullptr;
+  SCORE_CUDA_CHECK(cudaMalloc(&d_off, sizeof(int) * (n_traj + 1)));
+  cudaError_t e = cudaMalloc(&d_gt, sizeof(double) * std::max<size_t>(1, (size_t)P.P * P.d));
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
+  if (e == cudaSuccess) e = cudaMemcpy(d_gt, gt_pos, sizeof(double) * (size_t)P.P * P.d, cudaMemcpyDefault);
+  rc = SCORE_OK;
+  if (e == cudaSuccess)
+    rc = ate_launch(P.d, n_traj, d_off, h->out_poses, P.blk, P.d + 1, P.d, d_gt, align, rmse, R, t, nullptr);
+  cudaFree(d_off);
+  cudaFree(d_gt);
+  SCORE_CUDA_CHECK(e);
+  return rc;
+}
 
 extern "C" void score_destroy(ScoreHandle h) {
   if (!h) return;

@@ -16,8 +16,9 @@
 //   * incidences sorted by slot      -> diagonal blocks, one warp per slot run;
 //   * ranges sorted by slot pair     -> upper off-diagonal blocks, contiguous runs per warp;
 // so every block has exactly one owning warp, the summation order is fixed and no atomics are needed.
-// The nc x nc matrix is then inverted by symmetric sweeps (Gauss-Jordan in its symmetry-preserving form) with
-// the matrix held in registers (TS x TS tile per thread; one pivot row broadcast through shared memory per step).
+// The nc x nc matrix is then inverted by blocked symmetric sweeps (Gauss-Jordan in its symmetry-preserving form)
+// with the matrix held in registers (TS x TS tile per thread; per block of TS pivots one raw and one scaled row
+// panel broadcast through shared memory, one barrier).
 #pragma once
 #include "common.cuh"
 
@@ -272,9 +273,7 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
     return;
   }
   double *A = sm;                       // NP x NS
-  double *rowb = A + NP * NS;           // 2 x NP (NP * NS is even: 16-byte aligned)
-  double *pivb = rowb + 2 * NP;         // 2
-  double *stage = pivb + 2;             // NW x STAGE
+  double *stage = A + NP * NS;          // NW x STAGE (NP * NS is even: 16-byte aligned)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < NP * NS; i += kCoarseThreads) A[i] = 0.0;
   __syncthreads();
@@ -303,48 +302,80 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
       if (i == j && (i >= n || !(v > 0.0))) v = 1.0;  // padding / coordinate without curvature: identity
       Tl[r][c] = v;
     }
-  // ---- symmetric sweep of every pivot (SPD, no pivoting):  a_kk <- -1/p, a_ik <- a_ik/p, a_kj <- a_kj/p,
-  // a_ij <- a_ij - a_ik a_kj / p.  The matrix stays symmetric, so only the pivot ROW is broadcast (its owner is
-  // one warp) and the column factors are read from the same buffer.  Publishing p - 1 in place of p makes the
-  // generic rank-1 update produce the pivot row and column too; only a_kk itself is patched.  Result: -A^-1.
-  for (int k = 0; k < n; ++k) {
-    const int kt = k / TS, kl = k - kt * TS, buf = (k & 1) * NP;
+  // ---- blocked symmetric sweep (SPD, no pivoting), one TS x TS pivot block K per step:
+  //   A_KK <- -W,  A_KJ <- W A_KJ,  A_IK <- A_IK W,  A_IJ <- A_IJ - A_IK W A_KJ,      W = A_KK^-1,
+  // which is the composition of the TS scalar sweeps of the block, so after all blocks the tiles hold -A^-1.
+  // The pivot rows belong to one warp (ty == kt).  It inverts the pivot block with one lane per entry, then
+  // publishes two TS x NP panels: the raw rows (by symmetry also the column factors A_IK) and the scaled rows
+  // W A_KJ.  Publishing A_KK - I in place of A_KK makes the generic rank-TS update produce the new pivot rows
+  // and columns as well; only the pivot block itself is patched.  One barrier per TS pivots.
+  double *panel = stage;                // [2][2][TS][NP], double-buffered; the accumulation staging is idle now
+  double *wbuf = panel + 4 * TS * NP;   // [2][TS * TS]
+  static_assert(4 * TS * NP + 2 * TS * TS <= NW * CD::STAGE, "pivot panels must fit in the staging area");
+  const int nblk = (n + TS - 1) / TS;
+  for (int kt = 0; kt < nblk; ++kt) {
+    double *raw = panel + (kt & 1) * 2 * TS * NP, *scl = raw + TS * NP, *wb = wbuf + (kt & 1) * TS * TS;
     if (ty == kt) {  // warp-uniform
-      double rowv[TS];
-#pragma unroll
-      for (int r = 0; r < TS; ++r)
-        if (r == kl) {
-#pragma unroll
-          for (int c = 0; c < TS; ++c) rowv[c] = Tl[r][c];
-        }
       if (tx == kt) {
 #pragma unroll
-        for (int c = 0; c < TS; ++c)
-          if (c == kl) {
-            pivb[k & 1] = 1.0 / rowv[c];
-            rowv[c] -= 1.0;
-          }
-      }
+        for (int r = 0; r < TS; ++r) {
 #pragma unroll
-      for (int c = 0; c < TS; ++c) rowb[buf + tx * TS + c] = rowv[c];
+          for (int c = 0; c < TS; ++c) wb[r * TS + c] = Tl[r][c];
+          Tl[r][r] -= 1.0;
+        }
+      }
+      __syncwarp();
+      // W = A_KK^-1 by TS scalar sweeps, lane (i, j) holding entry (i, j) (lanes >= TS^2 idle along)
+      const int wi = (lane / TS) % TS, wj = lane % TS;
+      double w = (lane < TS * TS) ? wb[lane] : 1.0;
+#pragma unroll
+      for (int k = 0; k < TS; ++k) {
+        const double piv = __shfl_sync(0xffffffffu, w, k * TS + k);
+        const double wik = __shfl_sync(0xffffffffu, w, wi * TS + k), wkj = __shfl_sync(0xffffffffu, w, k * TS + wj);
+        const double inv = 1.0 / piv;
+        if (wi == k && wj == k)
+          w = -inv;
+        else if (wi == k || wj == k)
+          w *= inv;
+        else
+          w -= wik * wkj * inv;
+      }
+      __syncwarp();
+      if (lane < TS * TS) wb[lane] = -w;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < TS; ++r) {
+        double wr[TS];
+#pragma unroll
+        for (int k = 0; k < TS; ++k) wr[k] = wb[r * TS + k];
+#pragma unroll
+        for (int c = 0; c < TS; ++c) {
+          double sv = 0.0;
+#pragma unroll
+          for (int k = 0; k < TS; ++k) sv += wr[k] * Tl[k][c];
+          raw[r * NP + tx * TS + c] = Tl[r][c];
+          scl[r * NP + tx * TS + c] = sv;
+        }
+      }
     }
     __syncthreads();
-    const double inv = pivb[k & 1];
-    double rc[TS], cr[TS];
 #pragma unroll
-    for (int c = 0; c < TS; ++c) rc[c] = rowb[buf + tx * TS + c] * inv;
+    for (int k = 0; k < TS; ++k) {
+      double crk[TS], sck[TS];
 #pragma unroll
-    for (int r = 0; r < TS; ++r) cr[r] = rowb[buf + ty * TS + r];
+      for (int r = 0; r < TS; ++r) crk[r] = raw[k * NP + ty * TS + r];
 #pragma unroll
-    for (int r = 0; r < TS; ++r)
+      for (int c = 0; c < TS; ++c) sck[c] = scl[k * NP + tx * TS + c];
 #pragma unroll
-      for (int c = 0; c < TS; ++c) Tl[r][c] -= cr[r] * rc[c];
+      for (int r = 0; r < TS; ++r)
+#pragma unroll
+        for (int c = 0; c < TS; ++c) Tl[r][c] -= crk[r] * sck[c];
+    }
     if (ty == kt && tx == kt) {
 #pragma unroll
       for (int r = 0; r < TS; ++r)
 #pragma unroll
-        for (int c = 0; c < TS; ++c)
-          if (r == kl && c == kl) Tl[r][c] = -inv;
+        for (int c = 0; c < TS; ++c) Tl[r][c] = -wb[r * TS + c];
     }
   }
   // ---- write back (negated), symmetrise, store
@@ -378,7 +409,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_build(DevProblem P, S
 template <int D>
 inline size_t coarse_smem_bytes_d(int ts) {
   const size_t np = 32 * (size_t)ts;
-  return sizeof(double) * (np * (np + 1) + 2 * np + 2 + (size_t)(kCoarseThreads / 32) * CoarseDims<D>::STAGE);
+  return sizeof(double) * (np * (np + 1) + (size_t)(kCoarseThreads / 32) * CoarseDims<D>::STAGE);
 }
 inline size_t coarse_smem_bytes(int d, int ts) { return d == 2 ? coarse_smem_bytes_d<2>(ts) : coarse_smem_bytes_d<3>(ts); }
 inline int coarse_tile_size(int nmax) { return (nmax + 31) / 32; }

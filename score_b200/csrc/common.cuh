@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <type_traits>
 
 #include "../../include/score_b200.h"
 
@@ -180,6 +181,40 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* >= NT/32 *
   if (wid == 0) {
     out = (lane < NT / 32) ? smem[lane] : 0.0;
     out = warp_sum(out);
+  }
+  return out;
+}
+
+// Sixteen warp sums at once: every butterfly step halves the number of values a lane carries (the two halves
+// of the warp keep different values), 16 shuffles instead of 80.  Lane l returns the total of v[(l >> 1) & 15].
+// Fixed order, so bit-reproducible.
+__device__ __forceinline__ double warp_sum16(double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+    const bool up = lane & o;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Sixteen deterministic block sums with two barriers: total of v[i] is returned in thread i (i < 16), 0 elsewhere.
+template <int NT>
+__device__ __forceinline__ double block_sum16(double (&v)[16], double *smem /* >= 16 * NT/32 */) {
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double mine = warp_sum16(v);
+  __syncthreads();
+  if (!(lane & 1)) smem[(lane >> 1) * NW + wid] = mine;
+  __syncthreads();
+  double out = 0.0;
+  if (threadIdx.x < 16) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) out += smem[threadIdx.x * NW + w];
   }
   return out;
 }

@@ -53,6 +53,35 @@ __device__ __forceinline__ double barrier_eps(double q, double kap) {
   return e;
 }
 
+// The same root for G step sizes of one range at once (line search): the G Newton iterations are independent, so
+// running them in lockstep gives the scheduler G divisions to interleave instead of one dependent chain.  `tol` is
+// the relative step at which the iteration stops: phi_mu is the MINIMUM over rho, so its value is second-order
+// insensitive to the root (envelope) and, Newton converging quadratically, a last step below 1e-7 leaves the value
+// exact to rounding — the confirming iteration barrier_eps needs for the curvature terms is not needed here.
+template <int G>
+__device__ __forceinline__ void barrier_eps_group(const double (&qm)[G], double kap, double tol, double (&e)[G]) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const double sq = sqrt(qm[g] * qm[g] + 2.0 * kap);
+    e[g] = fmin((qm[g] >= 0.0) ? kap / (qm[g] + sq) : 0.5 * (sq - qm[g]), 1.0);
+  }
+  for (int it = 0; it < 6; ++it) {
+    bool all = true;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const double eg = e[g];
+      const double F = (qm[g] + eg) * eg * (2.0 - eg) - kap * (1.0 - eg);
+      const double dF = eg * (2.0 - eg) + (qm[g] + eg) * (2.0 - 2.0 * eg) + kap;
+      double ne = eg - F / dF;
+      if (!(ne > 0.0)) ne = 0.5 * eg;
+      ne = fmin(ne, 1.0);
+      all = all && (fabs(ne - eg) <= tol * eg);
+      e[g] = ne;
+    }
+    if (all) break;
+  }
+}
+
 // One range term at distance n: value phi_mu(n), tan = phi'/(2 w n), rad = phi''/(2 w).
 struct RangeTerm {
   double val, tan, rad;
@@ -200,7 +229,7 @@ __global__ void __launch_bounds__(kThreads) k_rowpass(DevProblem P, SolverVecs V
 // Plain rows are quadratic in a (three sums); range rows are evaluated per candidate.
 template <int D>
 __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
-  __shared__ double red[kThreads / 32];
+  __shared__ double red[16 * (kThreads / 32)];
   const BlockDesc bd = T.rb[bid];
   const int inst = bd.inst;
   if (st[inst].phase != PH_LS || st[inst].skip_ls || st[inst].eval_now) return;
@@ -239,20 +268,41 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
       }
       Bq *= lsc;
       C *= lsc * lsc;
+      if (!(rr > 0.0) || mu == 0.0) {  // dist == 0 / no barrier: closed forms, no root to find
 #pragma unroll
-      for (int c = 0; c < kNumCand; ++c) {
-        const double a = ls_candidate(c);  // compile-time constant; the ladder scale is folded into Bq, C
-        const double n = sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C)));
-        sums[3 + c] += range_value(n, rr, wk, mu);
+        for (int c = 0; c < kNumCand; ++c) {
+          const double a = ls_candidate(c);  // compile-time constant; the ladder scale is folded into Bq, C
+          sums[3 + c] += range_value(sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C))), rr, wk, mu);
+        }
+        sums[3 + kNumCand] += range_value(sqrt(A), rr, wk, mu);
+        continue;
       }
-      sums[3 + kNumCand] += range_value(sqrt(A), rr, wk, mu);
+      // kNumCand + 1 evaluation points (slot kNumCand: a = 0) in two lockstep groups
+      const double rinv = 1.0 / rr, wr2 = wk * rr * rr, kap = mu / wr2;
+      constexpr int G0 = (kNumCand + 2) / 2, G1 = kNumCand + 1 - G0;
+      auto eval_group = [&](auto gtag, const int c0) {
+        constexpr int G = decltype(gtag)::value;
+        double qm[G], e[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int c = c0 + g;
+          const double a = (c < kNumCand) ? ls_candidate(c) : 0.0;
+          qm[g] = fma(sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C))), rinv, -1.0);
+        }
+        barrier_eps_group<G>(qm, kap, 1e-7, e);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double gap = qm[g] + e[g];
+          sums[3 + c0 + g] += wr2 * gap * gap - mu * log(e[g] * (2.0 - e[g]));
+        }
+      };
+      eval_group(std::integral_constant<int, G0>{}, 0);
+      eval_group(std::integral_constant<int, G1>{}, G0);
     }
   }
-#pragma unroll
-  for (int i = 0; i < kLsSums; ++i) {
-    const double tot = block_sum<kThreads>(sums[i], red);
-    if (threadIdx.x == 0) V.part_ls[(size_t)bid * kLsSums + i] = tot;
-  }
+  static_assert(kLsSums == 16, "block_sum16 reduces exactly 16 sums");
+  const double tot = block_sum16<kThreads>(sums, red);
+  if (threadIdx.x < kLsSums) V.part_ls[(size_t)bid * kLsSums + threadIdx.x] = tot;
 }
 
 template <int D>

@@ -197,6 +197,23 @@ class ScoreSolver:
         self.d2h_bytes = poses.nbytes + rounded.nbytes + lms.nbytes + dist.nbytes
         return poses, rounded, lms, dist
 
+    def ate(self, gt_positions, traj_off=None, align: bool = True):
+        """Absolute trajectory error of the solved translations against ``gt_positions`` [P, d] on the device
+        (score_eval_ate): one trajectory per instance, or per ``traj_off`` range of the batch's global pose
+        numbering (e.g. ``lowering.chain_offsets(prob)`` for one trajectory per robot).  Returns
+        (rmse [n_traj], R [n_traj, d, d], t [n_traj, d]) with gt ~ R est + t."""
+        p = self.prob
+        d = p.dim
+        gt = _f64(gt_positions)
+        if gt.shape != (p.P, d):
+            raise ValueError(f"gt_positions must have shape {(p.P, d)}, got {gt.shape}")
+        off = None if traj_off is None else _i32(traj_off)
+        n = p.n_instances if off is None else len(off) - 1
+        rmse, R, t = np.empty(n), np.empty((n, d, d)), np.empty((n, d))
+        _check(self._lib.score_eval_ate(self._h, n, None if off is None else off.ctypes.data, gt.ctypes.data,
+                                        1 if align else 0, rmse.ctypes.data, R.ctypes.data, t.ctypes.data))
+        return rmse, R, t
+
     def internal(self, which: int, inst: int = 0) -> np.ndarray:
         """Solver internals of one instance (score_get_internal): flat float64 array."""
         n = C.c_int64()
@@ -328,3 +345,22 @@ def round_to_special_orthogonal_batch(mats: np.ndarray, device: int = 0) -> np.n
     out = np.empty_like(mats)
     _check(_lib.load().score_round_so(d, mats.shape[0], mats.ctypes.data, out.ctypes.data, device))
     return out
+
+
+def trajectory_ate(est, gt, traj_off=None, align: bool = True, device: int = 0):
+    """SE(d)-aligned absolute trajectory error of a batch of trajectories on the GPU (score_trajectory_ate).
+
+    est, gt: [n, d] positions (d = 2 or 3); traj_off: [n_traj + 1] offsets (default: one trajectory).
+    Returns (rmse [n_traj], R [n_traj, d, d], t [n_traj, d]) with gt ~ R est + t; empty trajectories give NaN."""
+    est, gt = _f64(est), _f64(gt)
+    if est.ndim != 2 or est.shape != gt.shape:
+        raise ValueError("est and gt must both be [n, d]")
+    d = est.shape[1]
+    off = _i32([0, est.shape[0]] if traj_off is None else traj_off)
+    if off.ndim != 1 or len(off) < 1 or (len(off) > 1 and int(off[-1]) > est.shape[0]):
+        raise ValueError("traj_off must be a 1-D offset array within the point arrays")
+    n = len(off) - 1
+    rmse, R, t = np.empty(n), np.empty((n, d, d)), np.empty((n, d))
+    _check(_lib.load().score_trajectory_ate(d, n, off.ctypes.data, est.ctypes.data, gt.ctypes.data, 1 if align else 0,
+                                            rmse.ctypes.data, R.ctypes.data, t.ctypes.data, device))
+    return rmse, R, t
