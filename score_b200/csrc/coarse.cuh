@@ -309,6 +309,12 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
   // publishes two TS x NP panels: the raw rows (by symmetry also the column factors A_IK) and the scaled rows
   // W A_KJ.  Publishing A_KK - I in place of A_KK makes the generic rank-TS update produce the new pivot rows
   // and columns as well; only the pivot block itself is patched.  One barrier per TS pivots.
+  // Layout of the scaled panel: the TS columns of lane tx are split into pairs, pair h of all lanes contiguous, so
+  // that every 128-bit shared load of a warp covers one contiguous 512-byte run (a 32-byte lane stride would make
+  // each quarter-warp hit every bank twice); the update loop is bound by shared-memory wavefronts, not by FP64.
+  auto scl_index = [](int lane_col, int c) {
+    return (TS % 2 == 0) ? (c >> 1) * (2 * 32) + lane_col * 2 + (c & 1) : lane_col * TS + c;
+  };
   double *panel = stage;                // [2][2][TS][NP], double-buffered; the accumulation staging is idle now
   double *wbuf = panel + 4 * TS * NP;   // [2][TS * TS]
   static_assert(4 * TS * NP + 2 * TS * TS <= NW * CD::STAGE, "pivot panels must fit in the staging area");
@@ -354,7 +360,7 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
 #pragma unroll
           for (int k = 0; k < TS; ++k) sv += wr[k] * Tl[k][c];
           raw[r * NP + tx * TS + c] = Tl[r][c];
-          scl[r * NP + tx * TS + c] = sv;
+          scl[r * NP + scl_index(tx, c)] = sv;
         }
       }
     }
@@ -365,7 +371,7 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
 #pragma unroll
       for (int r = 0; r < TS; ++r) crk[r] = raw[k * NP + ty * TS + r];
 #pragma unroll
-      for (int c = 0; c < TS; ++c) sck[c] = scl[k * NP + tx * TS + c];
+      for (int c = 0; c < TS; ++c) sck[c] = scl[k * NP + scl_index(tx, c)];
 #pragma unroll
       for (int r = 0; r < TS; ++r)
 #pragma unroll

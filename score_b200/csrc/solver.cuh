@@ -237,9 +237,7 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
   const double lsc = ls_scale(st[inst].ls_shift);
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
-  double sums[kLsSums];
-#pragma unroll
-  for (int i = 0; i < kLsSums; ++i) sums[i] = 0.0;
+  double sums[3] = {0.0, 0.0, 0.0};
   // plain (quadratic) rows of this block: relative-pose rows before the ranges, prior rows after them
   auto plain = [&](int r0, int r1) {
     for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
@@ -251,12 +249,20 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
   };
   plain(bd.i0, min(bd.i1, rr0));
   plain(max(bd.i0, rr1), bd.i1);
-  // range terms: one thread per range (a block never splits a range: kRowsPerBlock is a multiple of D)
+  // range terms: the kNumCand + 1 evaluation points of a range (slot kNumCand: a = 0) are split into two groups of
+  // GS, handled by an even / odd pair of threads — 2 x ranges work items per block, an equal number per thread
+  // (a block never splits a range: kRowsPerBlock is a multiple of D).  The odd group's last slot is idle padding.
+  constexpr int GS = 7;
+  static_assert(kNumCand == 12 && kLsSums == 16, "group layout: even threads c = 0..6, odd threads c = 7..11 and a = 0");
+  const int grp = threadIdx.x & 1;
+  double acc[GS];
+#pragma unroll
+  for (int g = 0; g < GS; ++g) acc[g] = 0.0;
   const int ra = max(bd.i0, rr0), rb = min(bd.i1, rr1);
   if (rb > ra) {
     const int nrng = (rb - ra) / D, kfirst = P.rng_off[inst] + (ra - rr0) / D;
-    for (int q = threadIdx.x; q < nrng; q += kThreads) {
-      const int row = ra + q * D, k = kfirst + q;
+    for (int it = threadIdx.x; it < 2 * nrng; it += kThreads) {  // it & 1 == grp (kThreads is even)
+      const int q = it >> 1, row = ra + q * D, k = kfirst + q;
       const double rr = P.rng_dist[k], wk = P.rng_w[k];
       double A = 0.0, Bq = 0.0, C = 0.0;
 #pragma unroll
@@ -268,45 +274,43 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
       }
       Bq *= lsc;
       C *= lsc * lsc;
+      double nn[GS];  // distance at this group's step sizes (compile-time constants; the ladder scale is in Bq, C)
+#pragma unroll
+      for (int g = 0; g < GS; ++g) {
+        const double a0 = ls_candidate(g), a1 = (GS + g < kNumCand) ? ls_candidate(GS + g) : 0.0;
+        const double a = grp ? a1 : a0;
+        nn[g] = sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C)));
+      }
       if (!(rr > 0.0) || mu == 0.0) {  // dist == 0 / no barrier: closed forms, no root to find
 #pragma unroll
-        for (int c = 0; c < kNumCand; ++c) {
-          const double a = ls_candidate(c);  // compile-time constant; the ladder scale is folded into Bq, C
-          sums[3 + c] += range_value(sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C))), rr, wk, mu);
-        }
-        sums[3 + kNumCand] += range_value(sqrt(A), rr, wk, mu);
+        for (int g = 0; g < GS; ++g) acc[g] += range_value(nn[g], rr, wk, mu);
         continue;
       }
-      // kNumCand + 1 evaluation points (slot kNumCand: a = 0) in two lockstep groups
       const double rinv = 1.0 / rr, wr2 = wk * rr * rr, kap = mu / wr2;
-      constexpr int G0 = (kNumCand + 2) / 2, G1 = kNumCand + 1 - G0;
-      auto eval_group = [&](auto gtag, const int c0) {
-        constexpr int G = decltype(gtag)::value;
-        double qm[G], e[G];
+      double qm[GS], e[GS];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int c = c0 + g;
-          const double a = (c < kNumCand) ? ls_candidate(c) : 0.0;
-          qm[g] = fma(sqrt(fmax(0.0, A + a * (2.0 * Bq + a * C))), rinv, -1.0);
-        }
-        barrier_eps_group<G>(qm, kap, 1e-7, e);
+      for (int g = 0; g < GS; ++g) qm[g] = fma(nn[g], rinv, -1.0);
+      barrier_eps_group<GS>(qm, kap, 1e-7, e);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const double gap = qm[g] + e[g];
-          sums[3 + c0 + g] += wr2 * gap * gap - mu * log(e[g] * (2.0 - e[g]));
-        }
-      };
-      eval_group(std::integral_constant<int, G0>{}, 0);
-      eval_group(std::integral_constant<int, G1>{}, G0);
+      for (int g = 0; g < GS; ++g) {
+        const double gap = qm[g] + e[g];
+        acc[g] += wr2 * gap * gap - mu * log(e[g] * (2.0 - e[g]));
+      }
     }
   }
-  static_assert(kLsSums == 16, "block_sum16 reduces exactly 16 sums");
-  const double tot = block_sum16<kThreads>(sums, red);
+  double v[kLsSums];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = sums[i];
+#pragma unroll
+  for (int g = 0; g < GS; ++g) v[3 + g] = grp ? 0.0 : acc[g];
+#pragma unroll
+  for (int g = 0; g < kLsSums - 3 - GS; ++g) v[3 + GS + g] = grp ? acc[g] : 0.0;
+  const double tot = block_sum16<kThreads>(v, red);
   if (threadIdx.x < kLsSums) V.part_ls[(size_t)bid * kLsSums + threadIdx.x] = tot;
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kThreads, 3) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, WL_LS, act, n_act);
