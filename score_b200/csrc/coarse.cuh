@@ -308,7 +308,7 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
   // The pivot rows belong to one warp (ty == kt).  It inverts the pivot block with one lane per entry, then
   // publishes two TS x NP panels: the raw rows (by symmetry also the column factors A_IK) and the scaled rows
   // W A_KJ.  Publishing A_KK - I in place of A_KK makes the generic rank-TS update produce the new pivot rows
-  // and columns as well; only the pivot block itself is patched.  One barrier per TS pivots.
+  // and columns as well; only the pivot block itself is patched.  Two barriers per TS pivots.
   // Layout of the scaled panel: the TS columns of lane tx are split into pairs, pair h of all lanes contiguous, so
   // that every 128-bit shared load of a warp covers one contiguous 512-byte run (a 32-byte lane stride would make
   // each quarter-warp hit every bank twice); the update loop is bound by shared-memory wavefronts, not by FP64.
@@ -319,52 +319,63 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
   double *wbuf = panel + 4 * TS * NP;   // [2][TS * TS]
   static_assert(4 * TS * NP + 2 * TS * TS <= NW * CD::STAGE, "pivot panels must fit in the staging area");
   const int nblk = (n + TS - 1) / TS;
-  for (int kt = 0; kt < nblk; ++kt) {
+  // reciprocal of a pivot: hardware seed + two Newton steps (the quotient routine is 2-3x the latency, and the
+  // TS dependent pivots of every block sit on the sweep's critical path)
+  auto rcp = [](double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+  };
+  // pivot warp of block kt: invert the pivot block, publish the raw and scaled row panels
+  auto factor_publish = [&](const int kt) {
     double *raw = panel + (kt & 1) * 2 * TS * NP, *scl = raw + TS * NP, *wb = wbuf + (kt & 1) * TS * TS;
-    if (ty == kt) {  // warp-uniform
-      if (tx == kt) {
-#pragma unroll
-        for (int r = 0; r < TS; ++r) {
-#pragma unroll
-          for (int c = 0; c < TS; ++c) wb[r * TS + c] = Tl[r][c];
-          Tl[r][r] -= 1.0;
-        }
-      }
-      __syncwarp();
-      // W = A_KK^-1 by TS scalar sweeps, lane (i, j) holding entry (i, j) (lanes >= TS^2 idle along)
-      const int wi = (lane / TS) % TS, wj = lane % TS;
-      double w = (lane < TS * TS) ? wb[lane] : 1.0;
-#pragma unroll
-      for (int k = 0; k < TS; ++k) {
-        const double piv = __shfl_sync(0xffffffffu, w, k * TS + k);
-        const double wik = __shfl_sync(0xffffffffu, w, wi * TS + k), wkj = __shfl_sync(0xffffffffu, w, k * TS + wj);
-        const double inv = 1.0 / piv;
-        if (wi == k && wj == k)
-          w = -inv;
-        else if (wi == k || wj == k)
-          w *= inv;
-        else
-          w -= wik * wkj * inv;
-      }
-      __syncwarp();
-      if (lane < TS * TS) wb[lane] = -w;
-      __syncwarp();
+    if (tx == kt) {
 #pragma unroll
       for (int r = 0; r < TS; ++r) {
-        double wr[TS];
 #pragma unroll
-        for (int k = 0; k < TS; ++k) wr[k] = wb[r * TS + k];
-#pragma unroll
-        for (int c = 0; c < TS; ++c) {
-          double sv = 0.0;
-#pragma unroll
-          for (int k = 0; k < TS; ++k) sv += wr[k] * Tl[k][c];
-          raw[r * NP + tx * TS + c] = Tl[r][c];
-          scl[r * NP + scl_index(tx, c)] = sv;
-        }
+        for (int c = 0; c < TS; ++c) wb[r * TS + c] = Tl[r][c];
+        Tl[r][r] -= 1.0;
       }
     }
-    __syncthreads();
+    __syncwarp();
+    // W = A_KK^-1 by TS scalar sweeps, lane (i, j) holding entry (i, j) (lanes >= TS^2 idle along)
+    const int wi = (lane / TS) % TS, wj = lane % TS;
+    double w = (lane < TS * TS) ? wb[lane] : 1.0;
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const double piv = __shfl_sync(0xffffffffu, w, k * TS + k);
+      const double wik = __shfl_sync(0xffffffffu, w, wi * TS + k), wkj = __shfl_sync(0xffffffffu, w, k * TS + wj);
+      const double inv = rcp(piv);
+      if (wi == k && wj == k)
+        w = -inv;
+      else if (wi == k || wj == k)
+        w *= inv;
+      else
+        w -= wik * wkj * inv;
+    }
+    __syncwarp();
+    if (lane < TS * TS) wb[lane] = -w;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < TS; ++r) {
+      double wr[TS];
+#pragma unroll
+      for (int k = 0; k < TS; ++k) wr[k] = wb[r * TS + k];
+#pragma unroll
+      for (int c = 0; c < TS; ++c) {
+        double sv = 0.0;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) sv += wr[k] * Tl[k][c];
+        raw[r * NP + tx * TS + c] = Tl[r][c];
+        scl[r * NP + scl_index(tx, c)] = sv;
+      }
+    }
+  };
+  // rank-TS update of this thread's tile with panel kt
+  auto apply_panel = [&](const int kt) {
+    const double *raw = panel + (kt & 1) * 2 * TS * NP, *scl = raw + TS * NP;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       double crk[TS], sck[TS];
@@ -377,11 +388,28 @@ __device__ __forceinline__ void coarse_build_body(DevProblem P, SolverVecs V, In
 #pragma unroll
         for (int c = 0; c < TS; ++c) Tl[r][c] -= crk[r] * sck[c];
     }
-    if (ty == kt && tx == kt) {
+  };
+  // Schedule.  The chain "apply panel kt to the rows of block kt+1, factor block kt+1" is the critical path; the
+  // other 31 warps' updates are bound by shared-memory wavefronts.  So after panel kt appears the next pivot warp
+  // updates its rows alone (second barrier), then factors block kt+1 into the other panel buffer WHILE the other
+  // warps apply panel kt.
+  if (ty == 0) factor_publish(0);
+  for (int kt = 0; kt < nblk; ++kt) {
+    __syncthreads();  // panel kt is published; every warp is done with panel kt-1 (its buffer is free again)
+    const bool next = (ty == kt + 1) && (kt + 1 < nblk);  // warp-uniform
+    if (next) apply_panel(kt);
+    __syncthreads();
+    if (next) {
+      factor_publish(kt + 1);
+    } else {
+      apply_panel(kt);
+      if (ty == kt && tx == kt) {
+        const double *wb = wbuf + (kt & 1) * TS * TS;
 #pragma unroll
-      for (int r = 0; r < TS; ++r)
+        for (int r = 0; r < TS; ++r)
 #pragma unroll
-        for (int c = 0; c < TS; ++c) Tl[r][c] = -wb[r * TS + c];
+          for (int c = 0; c < TS; ++c) Tl[r][c] = -wb[r * TS + c];
+      }
     }
   }
   // ---- write back (negated), symmetrise, store

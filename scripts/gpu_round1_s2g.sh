@@ -1,0 +1,7 @@
+#!/bin/bash
+# session 3, call g: two-barrier look-ahead schedule of the coarse sweep + fast pivot reciprocal
+mkdir -p gpurun_out
+( time timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coarse or bitwise or solution_parity or edge_case" ) > gpurun_out/pytest_gpu_s2g.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_s2g.log
+timeout 200 python scripts/profile_solve.py 1024 gpurun_out/profile_solve_s2g.json > gpurun_out/profile_solve_s2g.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_coarse_build" -s 1 -c 1 -o gpurun_out/prof_s2g python scripts/profile_solve.py 1024 x ncu=1 > gpurun_out/ncu_s2g.log 2>&1
+tail -5 gpurun_out/pytest_gpu_s2g.log; grep -A12 kernel_ms_total gpurun_out/profile_solve_s2g.json; grep "solve_ms\|cycles" gpurun_out/profile_solve_s2g.json
