@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -163,6 +164,7 @@ int wgrid(const ScoreHandle_ *h, long items, int per_sm) {
 // partial sums and are counted as zero.
 struct InstDims {
   double d, nnz, m, nz, K, P, nc;
+  bool fused = true;  // coarse application inside k_precond_fwd
 };
 double kernel_bytes_inst(int k, int mode, const InstDims &D) {
   const double d = D.d, blk = d * (d + 1), d1 = d + 1, nnz = D.nnz, m = D.m, nz = D.nz, K = D.K, Pn = D.P, nc = D.nc;
@@ -186,10 +188,10 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
       return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * nz;
     case KI_PRECOND_REV:  // r, ytmp out, G, M
       return ev ? 0.0 : 16.0 * nz + 8.0 * Pn * (blk + d1 * d1);
-    case KI_COARSE_APPLY:
-      return ev ? 0.0 : 8.0 * (nc * nc + 3.0 * nc);
-    case KI_PRECOND_FWD:  // ytmp, r, s out, G
-      return ev ? 0.0 : 24.0 * nz + 8.0 * Pn * blk;
+    case KI_COARSE_APPLY:  // inverse, rhs, solution out, scatter
+      return (ev || D.fused) ? 0.0 : 8.0 * (nc * nc + 3.0 * nc);
+    case KI_PRECOND_FWD:  // ytmp, r, s out, G (+ fused coarse application: inverse, rhs, scatter)
+      return ev ? 0.0 : 24.0 * nz + 8.0 * Pn * blk + (D.fused ? 8.0 * (nc * nc + 2.0 * nc) : 0.0);
     case KI_PUPDATE:  // s, p rw
       return ev ? 0.0 : 24.0 * nz;
     default:
@@ -307,6 +309,39 @@ extern "C" int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj
   return rc;
 }
 
+// Pinned host slots for the per-handle completion counters.  cudaMallocHost / cudaFreeHost are device-wide
+// synchronisation points: a handle created or destroyed while another handle's solve is running would stall behind
+// it (and stall it), so the slots come from one slab that is pinned once per process.
+namespace {
+struct PinnedSlots {
+  std::mutex mu;
+  int *slab = nullptr;
+  std::vector<int> free_list;
+  static constexpr int kSlots = 256, kInts = 2;
+  int *get() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!slab) {
+      if (cudaMallocHost((void **)&slab, sizeof(int) * kSlots * kInts) != cudaSuccess) {
+        slab = nullptr;
+        return nullptr;
+      }
+      for (int i = kSlots - 1; i >= 0; --i) free_list.push_back(i);
+    }
+    if (free_list.empty()) return nullptr;
+    const int i = free_list.back();
+    free_list.pop_back();
+    return slab + i * kInts;
+  }
+  bool put(int *p) {  // false: not one of ours
+    std::lock_guard<std::mutex> lk(mu);
+    if (!slab || p < slab || p >= slab + kSlots * kInts) return false;
+    free_list.push_back((int)(p - slab) / kInts);
+    return true;
+  }
+};
+PinnedSlots g_pinned;
+}  // namespace
+
 extern "C" void score_destroy(ScoreHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -318,7 +353,7 @@ extern "C" void score_destroy(ScoreHandle h) {
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   for (void *p : h->allocs) cudaFreeAsync(p, (cudaStream_t)0);
   if (h->sort_tmp) cudaFreeAsync(h->sort_tmp, (cudaStream_t)0);
-  if (h->h_ndone) cudaFreeHost(h->h_ndone);
+  if (h->h_ndone && !g_pinned.put(h->h_ndone)) cudaFreeHost(h->h_ndone);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -768,7 +803,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(h->out_round, (size_t)P.P * d * d)
   DA(h->out_dist, (size_t)P.K * h->dist_per)
 #undef DA
-  SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, 2 * sizeof(int)));
+  h->h_ndone = g_pinned.get();
+  if (!h->h_ndone) SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, 2 * sizeof(int)));
   for (auto &e : h->ev_done) SCORE_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // radix-sort scratch for the transpose
   int end_bit = 1;
@@ -777,7 +813,10 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
                                                    h->sort_perm, P.nnz, 0, end_bit, (cudaStream_t)0));
   SCORE_CUDA_CHECK(cudaMallocAsync(&h->sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 1, (cudaStream_t)0));
   SCORE_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  SCORE_CUDA_CHECK(cudaDeviceSynchronize());
+  // the allocations and uploads above are ordered on the default stream; the handle works on its own (non-blocking)
+  // stream.  Wait for the default stream only — a device-wide synchronisation would also wait for (and be delayed
+  // by) the solves of other handles that are running concurrently.
+  SCORE_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
   return SCORE_OK;
 }
 
@@ -887,13 +926,22 @@ static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaSt
   return SCORE_OK;
 }
 
+static bool coarse_apply_split() {
+  static const bool split = getenv("SCORE_SPLIT_COARSE_APPLY") && atoi(getenv("SCORE_SPLIT_COARSE_APPLY")) != 0;
+  return split;
+}
+
 // Preconditioner application s = P r (+ partial r.s), shared by the line-search and PCG ticks.
 template <int D>
 static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
   const DevProblem &P = h->P;
   if (pf) pf->mark(KI_PRECOND_REV);
   k_precond_rev<D><<<wgrid(h, (long)P.n_inst * (h->W.maxseg + 1), 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W);
-  if (h->c_nmax > 0) {
+  // small coarse spaces: the application A_c^-1 c is fused into the forward pass (SCORE_SPLIT_COARSE_APPLY=1 keeps
+  // the stand-alone kernel, for A/B measurements; both give the same bits)
+  const bool split = coarse_apply_split();
+  const bool fuse = h->c_nmax > 0 && !split;
+  if (h->c_nmax > 0 && split) {
     if (pf) pf->mark(KI_COARSE_APPLY);
     k_coarse_apply<D><<<wgrid(h, P.n_inst, 8), kCoarseApplyThreads, 0, st>>>(P, h->V, h->st, h->W);
   } else if (h->c_big) {
@@ -902,8 +950,8 @@ static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
     k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st);
   }
   if (pf) pf->mark(KI_PRECOND_FWD);
-  k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W);
-  return 2 + (h->c_nmax > 0 ? 1 : 0) + (h->c_big ? 2 : 0);
+  k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W, fuse);
+  return 2 + ((h->c_nmax > 0 && split) ? 1 : 0) + (h->c_big ? 2 : 0);
 }
 
 // Row-partitioned solve: sum a buffer over the ranks (out of place; every rank contributes its own rows only).
@@ -1194,7 +1242,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 4;
   const int grow_after = prm.cg_grow_after > 0 ? prm.cg_grow_after : (1 << 30);
   const int grow_every = prm.cg_grow_every > 0 ? prm.cg_grow_every : 8;
-  const int kernels_per_cg_tick = 7 + (h->c_nmax > 0 ? 1 : 0), kernels_per_ls_tick = 10 + (h->c_nmax > 0 ? 2 : 0) + 3;
+  const int n_capply = (h->c_nmax > 0 && coarse_apply_split()) ? 1 : 0;  // stand-alone coarse application kernel
+  const int kernels_per_cg_tick = 7 + n_capply, kernels_per_ls_tick = 10 + (h->c_nmax > 0 ? 1 : 0) + n_capply + 3;
   long ticks = 0, cycles = 0;
   double kernel_ms[12] = {0};
   long long kernel_count[12] = {0};
@@ -1290,6 +1339,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     D.K = h->rng_off[i + 1] - h->rng_off[i];
     D.P = h->pose_off[i + 1] - h->pose_off[i];
     D.nc = h->c_n[i];
+    D.fused = h->c_nmax > 0 && !coarse_apply_split();
     for (int k = 0; k < kNumKernels; ++k) {
       const double bcg = kernel_bytes_inst(k, TM_CG, D), bls = kernel_bytes_inst(k, TM_LS, D);
       // the first line-search tick only evaluates the start point (no direction yet)

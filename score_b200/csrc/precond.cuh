@@ -337,19 +337,53 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, Solve
 }
 
 // ---- s = P r, pass 2 (forward): Xh_p = sum_{q<=p} Y_q ;  s_p = Xh_p G_p ;  partial r.s
+// With `fuse` the coarse application y = A_c^-1 c (coarse.cuh) happens here instead of in a kernel of its own:
+// the CTA of free segment sl needs exactly the blk rows of y that start its prefix sum, the CTA of the pinned
+// first segment takes the landmark rows (-> s, partial r.s).  Every row is one warp's lane-strided dot product,
+// the same summation order as k_coarse_apply, so the two variants agree to the bit.
 template <int D>
-__device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s) {
-  constexpr int D1 = D + 1, NV = D * D1;
+__device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s,
+                                                 const bool fuse) {
+  constexpr int D1 = D + 1, NV = D * D1, NWS = kSegThreads / 32;
   __shared__ double wtot[kSegThreads / 32][NV];
   __shared__ double carry[NV];
   __shared__ double red[kSegThreads / 32];
+  __shared__ double ybase[NV];
+  __shared__ double ylm[kCoarseMax];
   const int tid = threadIdx.x;
   const int inst = P.seg_inst[s];
   if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
   const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
+  const int sl = s - P.seg_begin[inst];
+  const int nco = fuse ? P.c_n[inst] : 0;
+  if (nco > 0) {
+    const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
+    const double *__restrict__ cv = P.c_rhs + P.c_off[inst];
+    const int nb = P.c_nb[inst], lane = tid & 31, wid = tid >> 5;
+    const int row0 = (sl >= 1) ? (sl - 1) * NV : nb, nrow = (sl >= 1) ? NV : nco - nb;
+    for (int rr = wid; rr < nrow; rr += NWS) {
+      const double *__restrict__ arow = Ai + (size_t)(row0 + rr) * nco;
+      double a = 0.0;
+      for (int j = lane; j < nco; j += 32) a += __ldg(arow + j) * cv[j];
+      a = warp_sum(a);
+      if (lane == 0) (sl >= 1 ? ybase : ylm)[rr] = a;
+    }
+  }
   if (tid < NV) carry[tid] = 0.0;
   __syncthreads();
+  if (nco > 0 && sl == 0) {  // landmark block: s = y, partial r.s
+    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst], c0 = P.zoff[inst] + Pi * NV, nlm = nco - P.c_nb[inst];
+    double acc = 0.0;
+    for (int j = tid; j < nlm; j += kSegThreads) {
+      const double sv = ylm[j];
+      V.s[c0 + j] = sv;
+      acc += sv * V.r[c0 + j];
+    }
+    const double tot = block_sum<kSegThreads>(acc, red);
+    if (tid == 0) V.part_lm[inst] = tot;
+  }
+  const bool ystart = nco > 0 && sl >= 1;  // the segment's base block starts from the coarse solution
   double dot = 0.0;
   for (int t0 = 0; t0 < len; t0 += kSegThreads) {
     const int idx = t0 + tid;
@@ -359,9 +393,14 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
 #pragma unroll
     for (int c = 0; c < NV; ++c) v[c] = 0.0;
     if (valid) {
-      const double *yp = V.ytmp + colbase + (long)pg * NV;
+      double *yp = V.ytmp + colbase + (long)pg * NV;
+      if (ystart && idx == 0) {
 #pragma unroll
-      for (int c = 0; c < NV; ++c) v[c] = yp[c];
+        for (int c = 0; c < NV; ++c) yp[c] = v[c] = ybase[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) v[c] = yp[c];
+      }
     }
     cta_scan<NV>(v, wtot, carry);
     if (valid) {
@@ -393,13 +432,14 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
 }
 
 template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st, WorkLists W,
+                                                            const bool fuse) {
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxseg; item += gridDim.x) {
     const int inst = act[item / W.maxseg], s = P.seg_begin[inst] + (int)(item % W.maxseg);
-    if (s < P.seg_begin[inst + 1]) precond_fwd_body<D>(P, V, st, s);
+    if (s < P.seg_begin[inst + 1]) precond_fwd_body<D>(P, V, st, s, fuse);
     __syncthreads();
   }
 }

@@ -245,7 +245,7 @@ class ScoreSolver:
 
 
 class ScoreSolverGroup:
-    """A batch split into ``n_streams`` sub-batches, each with its own handle, CUDA stream and host thread.
+    """A batch split into sub-batches, each with its own handle and CUDA stream, solved by ``n_streams`` host threads.
 
     Independent instances never interact, so the sub-batches are solved concurrently: kernels of different
     streams fill each other's ramp-up / tail gaps on the GPU, and in the create -> solve -> read-back pipeline
@@ -253,14 +253,20 @@ class ScoreSolverGroup:
     Per-instance results are bit-identical to a single-handle solve (every instance is reduced in fixed order).
     """
 
-    def __init__(self, prob: LoweredProblem, n_streams: int = 2, device: int = 0, create: bool = True):
+    def __init__(self, prob: LoweredProblem, n_streams: int = 2, device: int = 0, create: bool = True,
+                 n_parts: int = 0):
+        """``n_parts`` (default: ``n_streams``) sub-batches are worked through by ``n_streams`` host threads, each
+        sub-batch on its own CUDA stream.  With more parts than streams the sub-batches start staggered, so the
+        sparsely occupied last cycles of one (a few slow instances) run under the dense first cycles of the next."""
         from concurrent.futures import ThreadPoolExecutor
 
-        n = max(1, min(int(n_streams), prob.n_instances))
+        n = max(1, min(int(n_parts) if n_parts > 0 else int(n_streams), prob.n_instances))
+        n_streams = max(1, min(int(n_streams), n))
         cuts = [round(j * prob.n_instances / n) for j in range(n + 1)]
         self.parts = [slice_instances(prob, cuts[j], cuts[j + 1]) for j in range(n)]
         self.prob, self.device, self.cuts = prob, device, cuts
-        self.pool = ThreadPoolExecutor(n)
+        self.n_streams = n_streams
+        self.pool = ThreadPoolExecutor(n_streams)
         self.solvers: List[Optional[ScoreSolver]] = [None] * n
         if create:
             self.solvers = list(self.pool.map(lambda part: ScoreSolver(part, device=device), self.parts))
@@ -318,22 +324,42 @@ class ScoreSolverGroup:
                           out[2][p.lm_off[a]:p.lm_off[b]], out[3][p.rng_off[a]:p.rng_off[b]]))
         return views
 
-    def run_pipelined(self, out=None, **kw):
+    def run_pipelined(self, out=None, steps: int = 1, **kw):
         """create -> solve -> read-back -> destroy of every sub-batch in its own thread (the end-to-end path).
-        Returns (stats, arrays, h2d_bytes, d2h_bytes)."""
+
+        ``steps`` > 1 repeats the whole batch that many times as ONE queue of sub-batch jobs (every job uploads its
+        inputs again and reads its results back): ``n_streams`` jobs solve at a time while one more thread already
+        runs the host-side ``score_create`` (table build + upload) of the next job, so the GPU does not idle during
+        the uploads — the way a long Monte-Carlo sweep is streamed through a GPU.
+        Returns (stats, arrays, h2d_bytes, d2h_bytes), the byte counts per step."""
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+
         kw.pop("stream", None)
         if out is None:
             out = tuple(np.empty(s) for s in self._shapes())
         views = self._views(out)
+        n = len(self.parts)
+        solving = threading.Semaphore(self.n_streams)
+        out_locks = [threading.Lock() for _ in range(n)]
 
-        def one(j):
+        def one(job):
+            j = job % n
             with ScoreSolver(self.parts[j], device=self.device) as s:
-                st = s.solve(**kw)
-                s.solution(out=views[j])
+                with solving:
+                    st = s.solve(**kw)
+                with out_locks[j]:
+                    s.solution(out=views[j])
                 return st, s.h2d_bytes, s.d2h_bytes
 
-        res = list(self.pool.map(one, range(len(self.parts))))
-        return self.merge_stats([r[0] for r in res]), out, sum(r[1] for r in res), sum(r[2] for r in res)
+        steps = max(1, int(steps))
+        if steps == 1:
+            res = list(self.pool.map(one, range(n)))
+        else:
+            with ThreadPoolExecutor(self.n_streams + 1) as pool:
+                res = list(pool.map(one, range(steps * n)))
+        return (self.merge_stats([r[0] for r in res]), out, sum(r[1] for r in res) // steps,
+                sum(r[2] for r in res) // steps)
 
 
 def round_to_special_orthogonal_batch(mats: np.ndarray, device: int = 0) -> np.ndarray:

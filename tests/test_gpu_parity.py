@@ -326,6 +326,19 @@ def test_stream_group_matches_single_handle_bitwise(built_lib, golden):
     assert np.array_equal(stg.instances["cg_iters"], st.instances["cg_iters"])
     for a, b, c in zip(ref, got, piped):
         assert np.array_equal(a, b) and np.array_equal(a, c)
+    # more sub-batches than host threads (staggered queue): same bits again
+    with ScoreSolverGroup(batch, n_streams=2, n_parts=5) as g:
+        assert len(g.parts) == 5 and g.n_streams == 2
+        stq = g.solve()
+        gotq = g.solution()
+        _, pipedq, h2d1, d2h1 = g.run_pipelined()
+        _, piped2, h2d2, d2h2 = g.run_pipelined(steps=3)  # three steps streamed as one job queue
+        assert (h2d2, d2h2) == (h2d1, d2h1) and d2h1 == d2h  # bytes are reported per step
+        for a, c in zip(ref, piped2):
+            assert np.array_equal(a, c)
+    assert stq.n_solved == 7 and np.array_equal(stq.instances["cg_iters"], st.instances["cg_iters"])
+    for a, b, c in zip(ref, gotq, pipedq):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
 
 
 def test_intermediate_iterates(built_lib, golden):

@@ -343,3 +343,29 @@ def test_slice_instances_inverts_concat():
                 assert x == y, f.name
     with pytest.raises(ValueError):
         slice_instances(c, 3, 3)
+
+
+def test_solver_group_partitions_a_batch_into_a_queue_of_sub_batches():
+    """ScoreSolverGroup(n_streams, n_parts): contiguous sub-batches that tile the batch; the host-thread count is
+    clamped to the number of parts, the part count to the number of instances (no device needed: create=False)."""
+    from score_b200 import generators
+    from score_b200.lowering import concat, lower_manhattan_arrays
+    from score_b200.solver import ScoreSolverGroup
+
+    probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=2, n_steps=6))
+             for i in range(7)]
+    batch = concat(probs)
+    g = ScoreSolverGroup(batch, n_streams=2, n_parts=4, create=False)
+    assert g.n_streams == 2 and len(g.parts) == 4 and g.cuts[0] == 0 and g.cuts[-1] == 7
+    assert sum(p.n_instances for p in g.parts) == 7 and all(p.n_instances >= 1 for p in g.parts)
+    assert sum(p.P for p in g.parts) == batch.P and sum(p.K for p in g.parts) == batch.K
+    for j, p in enumerate(g.parts):  # part j holds instances cuts[j] .. cuts[j+1] unchanged
+        a = g.cuts[j]
+        assert np.array_equal(p.rng_dist, batch.rng_dist[batch.rng_off[a]:batch.rng_off[g.cuts[j + 1]]])
+    g.close()
+    g = ScoreSolverGroup(batch, n_streams=3, create=False)  # default: one part per stream
+    assert g.n_streams == 3 and len(g.parts) == 3
+    g.close()
+    g = ScoreSolverGroup(batch, n_streams=16, n_parts=64, create=False)  # clamped to the instance count
+    assert len(g.parts) == 7 and g.n_streams == 7
+    g.close()
