@@ -210,6 +210,10 @@ int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj_off, const
                    double *rmse, double *R, double *t);
 
 void score_destroy(ScoreHandle h);
+/* Handles take their device memory, stream and events from process-wide caches that score_destroy refills (so
+ * that sweeps of similar problems create and destroy handles without any driver allocation call); this returns
+ * everything cached to the driver.  No reference counterpart. */
+void score_release_cached(void);
 const char *score_last_error(void);
 const char *score_version(void);
 

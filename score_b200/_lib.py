@@ -131,6 +131,7 @@ EXPORTED_SYMBOLS = [
     "score_trajectory_ate",
     "score_eval_ate",
     "score_destroy",
+    "score_release_cached",
     "score_last_error",
     "score_version",
 ]
@@ -191,6 +192,8 @@ def load() -> C.CDLL:
     lib.score_eval_ate.restype = C.c_int
     lib.score_destroy.argtypes = [C.c_void_p]
     lib.score_destroy.restype = None
+    lib.score_release_cached.argtypes = []
+    lib.score_release_cached.restype = None
     lib.score_last_error.restype = C.c_char_p
     lib.score_version.restype = C.c_char_p
     _lib = lib

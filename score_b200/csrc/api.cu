@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -92,7 +93,9 @@ struct ScoreHandle_ {
   double *cs_work = nullptr;
   int cs_lwork = 0;
   int *cs_info = nullptr;
-  std::vector<void *> allocs;
+  std::vector<std::pair<void *, size_t>> allocs;  // arena chunks (ResourceCache)
+  char *arena_ptr = nullptr;
+  size_t arena_left = 0, arena_hint = 1u << 20;
   cudaStream_t own_stream = nullptr;
   SolverCfg graph_cfg{};
   bool solved_once = false;
@@ -105,17 +108,115 @@ enum KernelId { KI_ROWPASS = 0, KI_LINESEARCH, KI_CTRL_A, KI_ROWUPDATE, KI_COARS
 
 namespace {
 
+// Device memory of a handle comes in large chunks that are sub-allocated linearly; released chunks, streams and
+// events go to process-wide caches instead of back to the driver.  In a sweep (handles of similar problems created
+// and destroyed continuously, while other handles are solving) score_create / score_destroy then make no
+// allocation, stream or event call at all: under concurrent graph launches every such call queues behind the
+// launches for the driver's context lock (measured ~1 ms each), and growing the memory pool stalls the whole device.
+struct ResourceCache {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> chunks[16];  // per device
+  std::vector<cudaStream_t> streams[16];
+  std::vector<cudaEvent_t> events[16];
+
+  // best fit among the cached chunks, else a new allocation (the only path that touches the driver)
+  cudaError_t get_chunk(int dev, size_t need, void **ptr, size_t *size) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &c = chunks[dev & 15];
+      int best = -1;
+      for (int i = 0; i < (int)c.size(); ++i)
+        if (c[i].second >= need && (best < 0 || c[i].second < c[best].second)) best = i;
+      if (best >= 0 && c[best].second <= 2 * need + (1u << 20)) {
+        *ptr = c[best].first;
+        *size = c[best].second;
+        c.erase(c.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    *size = need;
+    cudaError_t e = cudaMallocAsync(ptr, *size, (cudaStream_t)0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);  // usable on any stream from here on
+    return e;
+  }
+  void put_chunk(int dev, void *ptr, size_t size) {
+    std::lock_guard<std::mutex> lk(mu);
+    chunks[dev & 15].emplace_back(ptr, size);
+  }
+  cudaError_t get_stream(int dev, cudaStream_t *st) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &v = streams[dev & 15];
+      if (!v.empty()) {
+        *st = v.back();
+        v.pop_back();
+        return cudaSuccess;
+      }
+    }
+    return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+  }
+  void put_stream(int dev, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(mu);
+    streams[dev & 15].push_back(st);
+  }
+  cudaError_t get_event(int dev, cudaEvent_t *ev) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &v = events[dev & 15];
+      if (!v.empty()) {
+        *ev = v.back();
+        v.pop_back();
+        return cudaSuccess;
+      }
+    }
+    return cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+  }
+  void put_event(int dev, cudaEvent_t ev) {
+    std::lock_guard<std::mutex> lk(mu);
+    events[dev & 15].push_back(ev);
+  }
+  // give everything back to the driver (score_release_cached)
+  void release_all() {
+    std::lock_guard<std::mutex> lk(mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 16; ++d) {
+      if (chunks[d].empty() && streams[d].empty() && events[d].empty()) continue;
+      cudaSetDevice(d);
+      for (auto &c : chunks[d]) cudaFreeAsync(c.first, (cudaStream_t)0);
+      for (auto st : streams[d]) cudaStreamDestroy(st);
+      for (auto ev : events[d]) cudaEventDestroy(ev);
+      chunks[d].clear();
+      streams[d].clear();
+      events[d].clear();
+    }
+    cudaSetDevice(cur);
+  }
+};
+ResourceCache g_cache;
+
 template <typename T>
 int dalloc(ScoreHandle_ *h, T **ptr, size_t n) {
   *ptr = nullptr;
   if (n == 0) n = 1;
-  // stream-ordered allocation from the device's default pool (kept warm across handles, see pool_keep_warm)
-  cudaError_t e = cudaMallocAsync((void **)ptr, n * sizeof(T), (cudaStream_t)0);
-  if (e != cudaSuccess) {
-    g_score_last_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
-    return SCORE_ERR_ALLOC;
+  const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+  if (h->arena_left < bytes) {
+    void *chunk = nullptr;
+    size_t size = 0;
+    // first chunk: the handle's estimated footprint (create_impl); further chunks a quarter of it
+    const size_t want = std::max(bytes, h->allocs.empty() ? h->arena_hint : h->arena_hint / 4);
+    cudaError_t e = g_cache.get_chunk(h->device, want, &chunk, &size);
+    if (e != cudaSuccess) {
+      g_score_last_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+      return SCORE_ERR_ALLOC;
+    }
+    h->allocs.emplace_back(chunk, size);
+    h->arena_ptr = (char *)chunk;
+    h->arena_left = size;
   }
-  h->allocs.push_back((void *)*ptr);
+  *ptr = (T *)h->arena_ptr;
+  h->arena_ptr += bytes;
+  h->arena_left -= bytes;
   return SCORE_OK;
 }
 
@@ -202,6 +303,7 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
 }  // namespace
 
 extern "C" const char *score_last_error(void) { return g_score_last_error.c_str(); }
+extern "C" void score_release_cached(void) { g_cache.release_all(); }
 extern "C" const char *score_version(void) { return "score_b200 0.1.0 (sm_100a)"; }
 
 // ---- evaluation after the path: SE(d)-aligned absolute trajectory error, batched (evaluate.cuh) --------------
@@ -348,13 +450,12 @@ extern "C" void score_destroy(ScoreHandle h) {
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->cusolver) cusolverDnDestroy(h->cusolver);
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);  // nothing of this handle is in flight any more
   for (auto &e : h->ev_done)
-    if (e) cudaEventDestroy(e);
-  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-  for (void *p : h->allocs) cudaFreeAsync(p, (cudaStream_t)0);
-  if (h->sort_tmp) cudaFreeAsync(h->sort_tmp, (cudaStream_t)0);
+    if (e) g_cache.put_event(h->device, e);
+  for (auto &c : h->allocs) g_cache.put_chunk(h->device, c.first, c.second);
   if (h->h_ndone && !g_pinned.put(h->h_ndone)) cudaFreeHost(h->h_ndone);
-  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->own_stream) g_cache.put_stream(h->device, h->own_stream);
   delete h;
 }
 
@@ -536,7 +637,28 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
   return SCORE_OK;
 }
 
+// SCORE_TRACE_CREATE=1: print how long each phase of score_create took (host wall clock)
+struct CreateTrace {
+  bool on = getenv("SCORE_TRACE_CREATE") && atoi(getenv("SCORE_TRACE_CREATE")) != 0;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+  std::string line;
+  void mark(const char *what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s %.1f", what, std::chrono::duration<double, std::milli>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  ~CreateTrace() {
+    if (on)
+      fprintf(stderr, "[score_create] total %.1f ms:%s\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), line.c_str());
+  }
+};
+
 static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle_ *h) {
+  CreateTrace trace;
   const int d = desc->dim;
   if (d != 2 && d != 3) {
     g_score_last_error = "Value " + std::to_string(d) + " is not 2 or 3";
@@ -567,6 +689,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   }
   SCORE_CUDA_CHECK(cudaSetDevice(device));
   h->device = device;
+  // footprint estimate for the first arena chunk: operator in both orientations + sort scratch + solver vectors
+  h->arena_hint = (size_t)(40 * nnz + 60 * nz + 40 * m) + (1u << 20);
   {
     // keep freed blocks in the pool instead of returning them to the OS: create/destroy cycles of similar
     // problems (sweeps) then cost no cudaMalloc / cudaFree at all
@@ -594,6 +718,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   h->dist_per = (desc->relaxation == SCORE_RELAX_QCQP) ? d : 1;
   const int NI = P.n_inst;
   int rc;
+  trace.mark("checks");
   if ((rc = fetch_offsets(desc->pose_off, NI, desc->P, h->pose_off, "pose"))) return rc;
   if ((rc = fetch_offsets(desc->lm_off, NI, desc->L, h->lm_off, "landmark"))) return rc;
   if ((rc = fetch_offsets(desc->edge_off, NI, desc->E, h->edge_off, "edge"))) return rc;
@@ -700,6 +825,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.u, P.m)
   DA(V.bdz, P.m)
   DA(V.mk, (size_t)P.K * (d * (d + 1) / 2))
+  trace.mark("offsets+uploads");
   // coarse level: free segment bases + landmarks of every instance (dense, when it fits shared memory)
   {
     h->c_off.assign(NI + 1, 0);
@@ -732,7 +858,9 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     DA(P.c_Ainv, (size_t)moff)
     DA(P.c_rhs, h->c_off[NI])
     DA(P.c_sol, h->c_off[NI])
+    trace.mark("coarse-dims");
     if ((rc = build_coarse_tables(h, desc))) return rc;
+    trace.mark("coarse-tables");
   }
   // block tables
   std::vector<BlockDesc> rb, cb;
@@ -805,18 +933,25 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
 #undef DA
   h->h_ndone = g_pinned.get();
   if (!h->h_ndone) SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, 2 * sizeof(int)));
-  for (auto &e : h->ev_done) SCORE_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : h->ev_done) SCORE_CUDA_CHECK(g_cache.get_event(device, &e));
+  trace.mark("block-tables+allocs");
   // radix-sort scratch for the transpose
   int end_bit = 1;
   while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
   SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, P.cols, h->sort_keys, h->sort_idx,
                                                    h->sort_perm, P.nnz, 0, end_bit, (cudaStream_t)0));
-  SCORE_CUDA_CHECK(cudaMallocAsync(&h->sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 1, (cudaStream_t)0));
-  SCORE_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  {
+    char *tmp = nullptr;
+    if ((rc = dalloc(h, &tmp, h->sort_tmp_bytes))) return rc;
+    h->sort_tmp = tmp;
+  }
+  SCORE_CUDA_CHECK(g_cache.get_stream(device, &h->own_stream));
   // the allocations and uploads above are ordered on the default stream; the handle works on its own (non-blocking)
   // stream.  Wait for the default stream only — a device-wide synchronisation would also wait for (and be delayed
   // by) the solves of other handles that are running concurrently.
+  trace.mark("stream-create");
   SCORE_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
+  trace.mark("sync");
   return SCORE_OK;
 }
 
