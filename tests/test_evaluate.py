@@ -199,3 +199,65 @@ def test_handle_ate_on_monte_carlo_batch(built_lib):
         a, b = prob.pose_off[i], prob.pose_off[i + 1]
         r_o = so.align_trajectory(est[a:b], gt[a:b])[0]
         assert abs(rmse[i] - r_o) <= 1e-10
+
+
+# ---------------------------------------------------------------- golden fixture: ATE of the oracle optimum x*
+def _golden_ate():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "ate.json")) as f:
+        return json.load(f)
+
+
+def _xstar_translations(fg, extra):
+    from score_b200.evaluate import ground_truth_positions
+
+    d = int(fg.dimension)
+    gt = ground_truth_positions(fg)
+    est = np.asarray(extra["x_star"])[: len(gt) * d * (d + 1)].reshape(len(gt), d, d + 1)[:, :, d]
+    return est, gt
+
+
+@pytest.mark.parametrize("name", ["goats", "man4", "man1", "mc0_small"])
+def test_oracle_reproduces_golden_ate(golden, name):
+    """tests/golden/ate.json (make_ate_golden.py) from the stored optimum; GOATS also against the figure SURVEY.md
+    8(c) records for the reference's graph: the relaxed estimate sits ~58 m RMSE from ground truth after alignment."""
+    from oracle import score_oracle as so
+    from score_b200.evaluate import chain_offsets
+
+    fg, extra = golden(name)
+    est, gt = _xstar_translations(fg, extra)
+    ref = _golden_ate()[name]
+    rmse, R, t = so.align_trajectory(est, gt)
+    assert abs(rmse - ref["rmse"]) <= 1e-9 * max(1.0, ref["rmse"])
+    assert np.allclose(R, ref["R"], atol=1e-10) and np.allclose(t, ref["t"], atol=1e-7)
+    off = chain_offsets(fg)
+    per = [so.align_trajectory(est[a:b], gt[a:b])[0] for a, b in zip(off[:-1], off[1:])]
+    assert np.allclose(per, ref["rmse_per_chain"], rtol=1e-9)
+    if name == "goats":
+        assert 57.0 < rmse < 59.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["goats", "man4", "man1", "mc0_small"])
+def test_gpu_ate_matches_golden(built_lib, golden, name):
+    """CUDA path on the stored optimum == golden numbers; the GPU's own solve lands on the same error."""
+    from score_b200.evaluate import chain_offsets, evaluate_ate
+    from score_b200.solve_score import solve_score
+    from score_b200.solver import trajectory_ate
+
+    fg, extra = golden(name)
+    est, gt = _xstar_translations(fg, extra)
+    ref = _golden_ate()[name]
+    rmse, R, t = trajectory_ate(est, gt)
+    assert abs(rmse[0] - ref["rmse"]) <= 1e-9 * max(1.0, ref["rmse"])
+    assert np.allclose(R[0], ref["R"], atol=1e-9) and np.allclose(t[0], ref["t"], atol=1e-6)
+    assert abs(trajectory_ate(est, gt, align=False)[0][0] - ref["rmse_unaligned"]) <= 1e-9 * ref["rmse_unaligned"]
+    per = trajectory_ate(est, gt, chain_offsets(fg))[0]
+    assert np.allclose(per, ref["rmse_per_chain"], rtol=1e-9)
+    if name in ("goats", "man1"):  # single chains: the optimum is unique, the GPU solve reproduces its error
+        ev = evaluate_ate(solve_score(fg, "QCQP"), fg)
+        assert abs(ev["rmse"] - ref["rmse"]) <= 1e-3
