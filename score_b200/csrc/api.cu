@@ -175,9 +175,24 @@ struct ResourceCache {
     std::lock_guard<std::mutex> lk(mu);
     events[dev & 15].push_back(ev);
   }
+  // Instantiated cycle graphs of destroyed handles.  cudaGraphExecDestroy was seen to block for ~0.2 s now and then
+  // and to block every other thread's CUDA calls with it (e2e timelines, profiles/), so a sweep does not call it per
+  // handle: the executables are parked here and destroyed in bulk once many have piled up, or on release_all.
+  std::vector<cudaGraphExec_t> retired;
+  void retire_graph(cudaGraphExec_t g) {
+    std::vector<cudaGraphExec_t> victims;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      retired.push_back(g);
+      if (retired.size() >= 512) victims.swap(retired);
+    }
+    for (auto v : victims) cudaGraphExecDestroy(v);
+  }
   // give everything back to the driver (score_release_cached)
   void release_all() {
     std::lock_guard<std::mutex> lk(mu);
+    for (auto g : retired) cudaGraphExecDestroy(g);
+    retired.clear();
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 16; ++d) {
@@ -228,6 +243,24 @@ int upload(ScoreHandle_ *h, T **dst, const T *src, size_t n) {
   return SCORE_OK;
 }
 
+// Copy a caller array (host or device pointer) into host memory.  Host sources — the common case — are copied
+// with memcpy: a cudaMemcpy between two host buffers still goes through the driver and synchronises with the
+// default stream, which in a pipelined sweep means queueing behind other threads' launches.
+cudaError_t fetch_to_host(void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  cudaPointerAttributes at{};
+  const cudaError_t e = cudaPointerGetAttributes(&at, src);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // plain (unregistered) host memory on old drivers
+    memcpy(dst, src, bytes);
+    return cudaSuccess;
+  }
+  if (at.type == cudaMemoryTypeDevice) return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+  if (at.type == cudaMemoryTypeManaged) return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+  memcpy(dst, src, bytes);
+  return cudaSuccess;
+}
+
 int fetch_offsets(const int32_t *src, int n_inst, int64_t total, std::vector<int> &dst, const char *name) {
   dst.assign(n_inst + 1, 0);
   if (src == nullptr) {
@@ -238,7 +271,7 @@ int fetch_offsets(const int32_t *src, int n_inst, int64_t total, std::vector<int
     dst[1] = (int)total;
     return SCORE_OK;
   }
-  SCORE_CUDA_CHECK(cudaMemcpy(dst.data(), src, sizeof(int) * (n_inst + 1), cudaMemcpyDefault));
+  SCORE_CUDA_CHECK(fetch_to_host(dst.data(), src, sizeof(int) * (n_inst + 1)));
   if (dst[0] != 0 || dst[n_inst] != (int)total) {
     g_score_last_error = std::string(name) + " offsets do not span [0, total]";
     return SCORE_ERR_INVALID;
@@ -449,8 +482,8 @@ extern "C" void score_destroy(ScoreHandle h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->cusolver) cusolverDnDestroy(h->cusolver);
-  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);  // nothing of this handle is in flight any more
+  for (auto &kv : h->graphs) g_cache.retire_graph(kv.second);  // destroyed later, in bulk (see ResourceCache)
   for (auto &e : h->ev_done)
     if (e) g_cache.put_event(h->device, e);
   for (auto &c : h->allocs) g_cache.put_chunk(h->device, c.first, c.second);
@@ -569,11 +602,11 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
   std::vector<int> rng_a(P.K), rng_b(P.K), seg_ptr(P.n_seg + 1);
   std::vector<double> rng_w(P.K);
   if (P.K) {
-    SCORE_CUDA_CHECK(cudaMemcpy(rng_a.data(), desc->rng_a, sizeof(int) * P.K, cudaMemcpyDefault));
-    SCORE_CUDA_CHECK(cudaMemcpy(rng_b.data(), desc->rng_b, sizeof(int) * P.K, cudaMemcpyDefault));
-    SCORE_CUDA_CHECK(cudaMemcpy(rng_w.data(), desc->rng_w, sizeof(double) * P.K, cudaMemcpyDefault));
+    SCORE_CUDA_CHECK(fetch_to_host(rng_a.data(), desc->rng_a, sizeof(int) * P.K));
+    SCORE_CUDA_CHECK(fetch_to_host(rng_b.data(), desc->rng_b, sizeof(int) * P.K));
+    SCORE_CUDA_CHECK(fetch_to_host(rng_w.data(), desc->rng_w, sizeof(double) * P.K));
   }
-  SCORE_CUDA_CHECK(cudaMemcpy(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1), cudaMemcpyDefault));
+  SCORE_CUDA_CHECK(fetch_to_host(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1)));
   std::vector<CoarseInstTables> tabs(NI);
   {
     std::atomic<int> next(0);
@@ -581,7 +614,10 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
       for (int i = next.fetch_add(1); i < NI; i = next.fetch_add(1))
         coarse_tables_one(h, i, rng_a.data(), rng_b.data(), rng_w.data(), seg_ptr.data(), tabs[i]);
     };
-    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, NI / 8 + 1}));
+    // SCORE_CREATE_THREADS: upper bound of the table-building threads (default 16); in a pipelined sweep the threads
+    // that feed graph launches of the running solves share the host cores with them
+    static const int nt_max = getenv("SCORE_CREATE_THREADS") ? std::max(1, atoi(getenv("SCORE_CREATE_THREADS"))) : 16;
+    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), nt_max, NI / 8 + 1}));
     std::vector<std::thread> pool;
     for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
     worker();
@@ -739,8 +775,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     }
   // segments
   std::vector<int> seg_ptr(P.n_seg + 1), seg_inst(P.n_seg);
-  SCORE_CUDA_CHECK(cudaMemcpy(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1), cudaMemcpyDefault));
-  SCORE_CUDA_CHECK(cudaMemcpy(seg_inst.data(), desc->seg_inst, sizeof(int) * P.n_seg, cudaMemcpyDefault));
+  SCORE_CUDA_CHECK(fetch_to_host(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1)));
+  SCORE_CUDA_CHECK(fetch_to_host(seg_inst.data(), desc->seg_inst, sizeof(int) * P.n_seg));
   if (seg_ptr[0] != 0 || seg_ptr[P.n_seg] != P.P) {
     g_score_last_error = "seg_ptr does not span the poses";
     return SCORE_ERR_INVALID;
@@ -908,9 +944,9 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     W.maxrb = maxrb;
     W.maxcb = maxcb;
     W.maxseg = maxseg;
-    cudaDeviceProp prop;
-    SCORE_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    h->n_sm = prop.multiProcessorCount;
+    // (cudaGetDeviceProperties fills the whole property struct through the driver and takes milliseconds — far
+    // longer when other threads are launching work; one attribute is all that is needed)
+    SCORE_CUDA_CHECK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
   }
   h->red_count = 3 * rb.size() + (size_t)P.nz;
   DA(h->red_send, h->red_count)
@@ -938,8 +974,21 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   // radix-sort scratch for the transpose
   int end_bit = 1;
   while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
-  SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, P.cols, h->sort_keys, h->sort_idx,
-                                                   h->sort_perm, P.nnz, 0, end_bit, (cudaStream_t)0));
+  {
+    // the size query walks through the runtime (device / kernel attribute look-ups); cache it per (nnz, end_bit)
+    static std::mutex mu;
+    static std::map<std::pair<long long, int>, size_t> known;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair((long long)P.nnz, end_bit);
+    auto it = known.find(key);
+    if (it == known.end()) {
+      size_t bytes = 0;
+      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, P.cols, h->sort_keys, h->sort_idx, h->sort_perm,
+                                                       P.nnz, 0, end_bit, (cudaStream_t)0));
+      it = known.emplace(key, bytes).first;
+    }
+    h->sort_tmp_bytes = it->second;
+  }
   {
     char *tmp = nullptr;
     if ((rc = dalloc(h, &tmp, h->sort_tmp_bytes))) return rc;

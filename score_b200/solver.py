@@ -324,6 +324,15 @@ class ScoreSolverGroup:
                           out[2][p.lm_off[a]:p.lm_off[b]], out[3][p.rng_off[a]:p.rng_off[b]]))
         return views
 
+    def prewarm(self, extra: int = 1) -> None:
+        """Create and destroy ``n_streams + 1 + extra`` handles at once, so that the library's chunk / stream / event
+        caches hold enough for the streamed pipeline plus a spare set (a handle that has to go to the driver for
+        memory while others solve costs hundreds of milliseconds)."""
+        k = self.n_streams + 1 + max(0, int(extra))
+        hs = [ScoreSolver(self.parts[i % len(self.parts)], device=self.device) for i in range(k)]
+        for h in hs:
+            h.close()
+
     def run_pipelined(self, out=None, steps: int = 1, **kw):
         """create -> solve -> read-back -> destroy of every sub-batch in its own thread (the end-to-end path).
 
@@ -341,11 +350,14 @@ class ScoreSolverGroup:
         views = self._views(out)
         n = len(self.parts)
         solving = threading.Semaphore(self.n_streams)
+        creating = threading.Lock()  # one score_create at a time: concurrent creates only contend (host cores, driver)
         out_locks = [threading.Lock() for _ in range(n)]
 
         def one(job):
             j = job % n
-            with ScoreSolver(self.parts[j], device=self.device) as s:
+            with creating:
+                s = ScoreSolver(self.parts[j], device=self.device)
+            with s:
                 with solving:
                     st = s.solve(**kw)
                 with out_locks[j]:
