@@ -425,10 +425,10 @@ def run_gpu_arm(args, rank, local_rank, world):
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
-        _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, kkt_tol=KKT_TOL)
-        g2.close()
+        _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, kkt_tol=KKT_TOL)  # returns after the last read-back
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        g2.close()
         if world > 1:
             dist.barrier()
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)

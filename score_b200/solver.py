@@ -267,6 +267,7 @@ class ScoreSolverGroup:
         self.prob, self.device, self.cuts = prob, device, cuts
         self.n_streams = n_streams
         self.pool = ThreadPoolExecutor(n_streams)
+        self.pipe_pool = None
         self.solvers: List[Optional[ScoreSolver]] = [None] * n
         if create:
             self.solvers = list(self.pool.map(lambda part: ScoreSolver(part, device=device), self.parts))
@@ -277,6 +278,9 @@ class ScoreSolverGroup:
                 s.close()
         self.solvers = [None] * len(self.parts)
         self.pool.shutdown(wait=True)
+        if self.pipe_pool is not None:
+            self.pipe_pool.shutdown(wait=True)
+            self.pipe_pool = None
 
     def __enter__(self):
         return self
@@ -368,8 +372,9 @@ class ScoreSolverGroup:
         if steps == 1:
             res = list(self.pool.map(one, range(n)))
         else:
-            with ThreadPoolExecutor(self.n_streams + 1) as pool:
-                res = list(pool.map(one, range(steps * n)))
+            if self.pipe_pool is None:  # kept for the life of the group: no thread start-up / tear-down per call
+                self.pipe_pool = ThreadPoolExecutor(self.n_streams + 1)
+            res = list(self.pipe_pool.map(one, range(steps * n)))
         return (self.merge_stats([r[0] for r in res]), out, sum(r[1] for r in res) // steps,
                 sum(r[2] for r in res) // steps)
 
