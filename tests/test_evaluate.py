@@ -261,3 +261,20 @@ def test_gpu_ate_matches_golden(built_lib, golden, name):
     if name in ("goats", "man1"):  # single chains: the optimum is unique, the GPU solve reproduces its error
         ev = evaluate_ate(solve_score(fg, "QCQP"), fg)
         assert abs(ev["rmse"] - ref["rmse"]) <= 1e-3
+
+
+def test_trajectory_ate_argument_errors_need_no_device(built_lib):
+    """The C entry point validates its arguments before touching the device (error behaviour of the library:
+    ValueError for invalid input), and zero trajectories are a no-op."""
+    from score_b200.solver import trajectory_ate
+
+    with pytest.raises(ValueError):
+        trajectory_ate(np.zeros((4, 4)), np.zeros((4, 4)))  # dimension 4
+    with pytest.raises(ValueError):
+        trajectory_ate(np.zeros((4, 2)), np.zeros((4, 2)), [0, 3, 2])  # offsets not monotone
+    with pytest.raises(ValueError):
+        trajectory_ate(np.zeros((4, 2)), np.zeros((5, 2)))  # shapes differ
+    with pytest.raises(ValueError):
+        trajectory_ate(np.zeros((4, 2)), np.zeros((4, 2)), [0, 9])  # offsets beyond the arrays
+    rmse, R, t = trajectory_ate(np.zeros((0, 2)), np.zeros((0, 2)), [0])
+    assert rmse.shape == (0,) and R.shape == (0, 2, 2) and t.shape == (0, 2)
