@@ -369,3 +369,77 @@ def test_solver_group_partitions_a_batch_into_a_queue_of_sub_batches():
     g = ScoreSolverGroup(batch, n_streams=16, n_parts=64, create=False)  # clamped to the instance count
     assert len(g.parts) == 7 and g.n_streams == 7
     g.close()
+
+
+def test_streamed_pipeline_queue_semantics(monkeypatch):
+    """ScoreSolverGroup.run_pipelined(steps=K) without a device (ScoreSolver replaced by a recorder): K x parts jobs,
+    one score_create at a time, at most n_streams solves at a time, one more job may already be created while they
+    run, byte counts reported per step, every job read back into its own part's view."""
+    import threading
+    import time
+
+    from score_b200 import generators, solver as solver_mod
+    from score_b200.lowering import concat, lower_manhattan_arrays
+
+    probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=2, n_steps=6))
+             for i in range(4)]
+    batch = concat(probs)
+    lock = threading.Lock()
+    state = {"creating": 0, "max_creating": 0, "solving": 0, "max_solving": 0, "alive": 0, "max_alive": 0, "jobs": 0,
+             "readbacks": []}
+
+    class FakeSolver:
+        def __init__(self, prob, device=0):
+            with lock:
+                state["creating"] += 1
+                state["max_creating"] = max(state["max_creating"], state["creating"])
+                state["alive"] += 1
+                state["max_alive"] = max(state["max_alive"], state["alive"])
+            time.sleep(0.01)
+            self.prob, self.h2d_bytes, self.d2h_bytes = prob, 100 * prob.n_instances, 0
+            with lock:
+                state["creating"] -= 1
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            self.close()
+
+        def close(self):
+            with lock:
+                state["alive"] -= 1
+
+        def solve(self, **kw):
+            with lock:
+                state["solving"] += 1
+                state["max_solving"] = max(state["max_solving"], state["solving"])
+                state["jobs"] += 1
+            time.sleep(0.03)
+            with lock:
+                state["solving"] -= 1
+            n = self.prob.n_instances
+            inst = np.zeros(n, dtype=solver_mod._INST_DTYPE)
+            inst["solved"] = 1
+            z = np.zeros(len(solver_mod.KERNEL_NAMES))
+            return solver_mod.SolveStats(n, n, 5, 7, 0.0, 0.0, 1.0, 0.0, 1.0, 0, 0, 0, 0.0, inst, kernel_ms=z,
+                                         kernel_bytes=z, kernel_count=z, kernel_bytes_total=z, cycles=1)
+
+        def solution(self, out=None):
+            out[0][...] = float(self.prob.n_instances)  # mark the view of this part
+            self.d2h_bytes = 10 * self.prob.n_instances
+            with lock:
+                state["readbacks"].append(out[0].shape[0])
+            return out
+
+    monkeypatch.setattr(solver_mod, "ScoreSolver", FakeSolver)
+    g = solver_mod.ScoreSolverGroup(batch, n_streams=2, n_parts=2, create=False)
+    stats, out, h2d, d2h = g.run_pipelined(steps=3)
+    g.close()
+    assert state["jobs"] == 6 and stats.n_instances == 12 and stats.n_solved == 12  # 3 steps x 2 parts x 2 instances
+    assert state["max_creating"] == 1
+    assert state["max_solving"] <= 2
+    assert state["max_alive"] <= 3  # two solving + one created ahead
+    assert (h2d, d2h) == (100 * 4, 10 * 4)  # per step
+    assert np.all(out[0] == 2.0)  # every pose row was written by a 2-instance part
+    assert sorted(state["readbacks"]) == sorted([g.parts[0].P, g.parts[1].P] * 3)
