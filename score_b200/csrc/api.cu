@@ -136,6 +136,17 @@ struct ResourceCache {
     }
     *size = need;
     cudaError_t e = cudaMallocAsync(ptr, *size, (cudaStream_t)0);
+    if (e == cudaErrorMemoryAllocation) {
+      // out of memory while chunks of other sizes sit unused in the cache: give those back and try once more
+      cudaGetLastError();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &c : chunks[dev & 15]) cudaFreeAsync(c.first, (cudaStream_t)0);
+        chunks[dev & 15].clear();
+      }
+      cudaStreamSynchronize((cudaStream_t)0);
+      e = cudaMallocAsync(ptr, *size, (cudaStream_t)0);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);  // usable on any stream from here on
     return e;
   }
