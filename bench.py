@@ -28,6 +28,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The CPU legs run ONE oracle solve per host core: BLAS / OpenMP pools inside every worker would oversubscribe the
+# cores many times over.  The limits must be in the environment before numpy / scipy load their libraries (setting
+# them inside an already forked worker has no effect); the pool initializer below clamps them again at run time.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"
+
 import numpy as np  # noqa: E402
 
 METRIC = "batched solves/sec (each SOCP/QCQP instance solved to 1e-6 relative KKT)"
@@ -51,6 +57,13 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2, help="sub-batches per GPU solved concurrently on their own streams")
     ap.add_argument("--parts", type=int, default=0, help="sub-batches per GPU (default: --streams); more parts than "
                     "streams staggers them so that one sub-batch's sparse tail runs under the next one's dense start")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --instances per GPU (the default, BASELINE configs[3] per GPU); strong: --instances in total, "
+                    "split over the ranks")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the single-graph time-to-solve table")
+    ap.add_argument("--no-config5", action="store_true", help="skip the large 3D graph in the per-config table")
+    ap.add_argument("--parity-kkt", type=int, default=4, help="instances of the parity sample whose GPU solution is "
+                    "re-certified with the oracle's KKT evaluator")
     return ap.parse_args()
 
 
@@ -88,8 +101,16 @@ def make_batch(first, count, robots, poses):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (interior-point restatement of the reference's Gurobi barrier solve)
 # ------------------------------------------------------------------------------------------------
+def _cpu_worker_init():
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=1)
+    except Exception:  # the environment variables above already did the job
+        pass
+
+
 def _cpu_solve_one(args):
-    os.environ["OMP_NUM_THREADS"] = "1"
     seed, robots, poses = args
     from oracle import score_oracle as so  # bench.py's CPU legs are allowed to execute the oracle
     from score_b200 import generators
@@ -97,10 +118,19 @@ def _cpu_solve_one(args):
     fg = generators.manhattan_2d(seed, n_robots=robots, n_steps=poses)
     t0 = time.perf_counter()
     prob = so.assemble(fg, so.QCQP)
-    sol = so.solve_qcqp_barrier(prob, mu_final=1e-9)
+    # follow the central path until the polished point certifies (rel KKT <= 1e-6), like the GPU path does
+    sol = so.solve_qcqp_barrier(prob, mu_final=1e-14, stop_kkt=KKT_TOL)
     x = so.polish_distances(prob, sol.x)
+    dt = time.perf_counter() - t0
     kkt = so.kkt_qcqp(prob, x)["rel_kkt"]
-    return time.perf_counter() - t0, kkt, sol.objective
+    return dt, kkt, so.objective(prob, x)
+
+
+def cpu_pool(cores):
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    return ProcessPoolExecutor(cores, mp_context=mp.get_context("fork"), initializer=_cpu_worker_init)
 
 
 def cpu_step(pool, seeds, robots, poses):
@@ -133,7 +163,7 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or cores
     times = []
-    with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
+    with cpu_pool(cores) as pool:
         # warm-up: spin the pool up on a reduced sample (tiny instances), untimed
         for _ in range(max(1, args.warmup)):
             cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(cores)], 4, 25)
@@ -159,14 +189,16 @@ def run_reference_arm(args, rank, world):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(args, sample_note=f"{sample} instances per step"),
+        "config": workload_config(args, sample_note=f"a bounded sample of the sweep: {sample} instances per step, one per "
+                                  "host core (a rate, so the sample size does not enter it)"),
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
             "cores": cores,
             "kind": "port",
             "sample": f"{sample} sweep instances per step ({args.robots} robots x {args.poses} poses), one per process, "
-            f"log-barrier Newton + SuperLU (oracle/score_oracle.py) to rel KKT <= 1e-6 (max seen {max(kkts):.1e}); "
+            f"log-barrier Newton + SuperLU (oracle/score_oracle.py), 1 thread per process, path followed until the point "
+            f"certifies rel KKT <= 1e-6 (max seen {max(kkts):.1e}, {sum(k <= KKT_TOL for k in kkts)}/{len(kkts)} certified); "
             f"cpu: {cpu_model()}",
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,7 +209,7 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(args, sample_note=None):
     cfg = {
-        "workload": f"monte_carlo_sweep (BASELINE configs[3]): {args.instances} instances/GPU x "
+        "workload": f"monte_carlo_sweep (BASELINE configs[3]): {args.instances} instances{' in total' if args.scaling == 'strong' else '/GPU'} x "
         f"({args.robots} robots x {args.poses} poses, 6 landmarks, ~{int(31 * args.poses * args.robots / 20)} ranges), "
         "2D, QCQP relaxation, seeds 20221003+i, solved to 1e-6 rel KKT",
         "instances_per_gpu": args.instances,
@@ -194,6 +226,55 @@ def workload_config(args, sample_note=None):
     if sample_note:
         cfg["reference_sample"] = sample_note
     return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# per-config time-to-solve: BASELINE configs 1-3 from the committed fixtures, config 5 generated
+# ------------------------------------------------------------------------------------------------
+def load_per_config_inputs(args):
+    from score_b200 import generators
+    from score_b200.graph_io import load_graph_npz
+    from score_b200.lowering import lower_factor_graph, lower_grid3d_arrays
+
+    out = []
+    for cfg, name in (("config1_goats14", "goats"), ("config2_manhattan_robotA", "man1"), ("config3_manhattan_4robot", "man4")):
+        fg, extra = load_graph_npz(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        out.append((cfg, lower_factor_graph(fg), float(extra["f_star"])))
+    if not args.no_config5:
+        arr = generators.grid_3d_arrays(generators.MC_BASE_SEED, n_robots=100, n_steps=1000, grid=100, n_landmarks=1000,
+                                        n_ranges=1000000)
+        out.append(("config5_large3d_100k_poses_1M_ranges", lower_grid3d_arrays(arr), None))
+    return out
+
+
+def run_per_config(inputs, device):
+    from score_b200.solver import ScoreSolver
+
+    table = {}
+    for cfg, prob, f_star in inputs:
+        reps = 1 if prob.P > 50000 else 5
+        with ScoreSolver(prob, device=device) as s:
+            s.solve(kkt_tol=KKT_TOL)  # warm-up: graph capture, caches
+            sts = [s.solve(kkt_tol=KKT_TOL) for _ in range(reps)]
+        st = sorted(sts, key=lambda t: t.total_ms)[len(sts) // 2]
+        rec = st.instances[0]
+        table[cfg] = {
+            "time_to_solve_ms": st.total_ms,
+            "solve_ms": st.solve_ms,
+            "assemble_ms": st.assemble_ms,
+            "setup_ms": st.setup_ms,
+            "solved": int(rec["solved"]),
+            "rel_kkt": float(rec["rel_kkt"]),
+            "objective": float(rec["objective"]),
+            "rel_obj_gap_vs_fixture": (abs(float(rec["objective"]) - f_star) / max(1.0, abs(f_star))) if f_star is not None else None,
+            "newton": int(rec["newton_iters"]),
+            "cg": int(rec["cg_iters"]),
+            "ticks": int(st.ticks),
+            "us_per_tick": 1e3 * st.solve_ms / max(1, st.ticks),
+            "gbs_algorithmic": st.algorithmic_bytes / (st.solve_ms * 1e-3) / 1e9 if st.solve_ms > 0 else None,
+            "poses": int(prob.P), "ranges": int(prob.K), "dim": int(prob.dim),
+        }
+    return table
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,6 +344,7 @@ class ClockSampler:
 def run_gpu_arm(args, rank, local_rank, world):
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork safety)
     cpu_baseline = None
+    cpu_results = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
@@ -271,18 +353,20 @@ def run_gpu_arm(args, rank, local_rank, world):
 
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or cores
-        with ProcessPoolExecutor(cores, mp_context=mp.get_context("fork")) as pool:
+        with cpu_pool(cores) as pool:
             cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(cores)], 4, 25)  # pool spin-up
-            dt, res = cpu_step(pool, [generators.MC_BASE_SEED + i for i in range(sample)], args.robots, args.poses)
+            dt, res = cpu_step(pool, [generators.MC_BASE_SEED + args.first_instance + i for i in range(sample)],
+                               args.robots, args.poses)
+        cpu_results = res
         cpu_baseline = {
             "value": sample / dt,
             "unit": UNIT,
             "cores": cores,
             "kind": "port",
             "sample": f"{sample} sweep instances (seeds 20221003..+{sample - 1}), one per process over {cores} cores, "
-            f"log-barrier Newton + SuperLU (oracle/score_oracle.py) to rel KKT <= 1e-6 "
-            f"(max seen {max(r[1] for r in res):.1e}); wall {dt:.1f} s; mean per-instance {np.mean([r[0] for r in res]):.1f} s; "
-            f"cpu: {cpu_model()}",
+            f"log-barrier Newton + SuperLU (oracle/score_oracle.py), 1 thread per process, path followed until the point "
+            f"certifies rel KKT <= 1e-6 (max seen {max(r[1] for r in res):.1e}); wall {dt:.1f} s; mean per-instance "
+            f"{np.mean([r[0] for r in res]):.1f} s; cpu: {cpu_model()}",
         }
 
     import torch
@@ -294,7 +378,15 @@ def run_gpu_arm(args, rank, local_rank, world):
     from score_b200.solver import KERNEL_NAMES, ScoreSolver, ScoreSolverGroup
 
     # generate the shard before CUDA is initialised (the generator forks worker processes)
-    prob = make_batch(args.first_instance + rank * args.instances, args.instances, args.robots, args.poses)
+    if args.scaling == "strong":  # --instances in total: rank r takes the r-th contiguous slice of the sweep
+        lo, hi = (args.instances * rank) // world, (args.instances * (rank + 1)) // world
+    else:
+        lo, hi = rank * args.instances, (rank + 1) * args.instances
+    n_local = hi - lo
+    prob = make_batch(args.first_instance + lo, n_local, args.robots, args.poses)
+    per_config = None
+    if rank == 0 and world == 1 and not args.no_per_config:
+        per_config_inputs = load_per_config_inputs(args)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -346,8 +438,38 @@ def run_gpu_arm(args, rank, local_rank, world):
     else:
         n_solved_all, launches_all = n_solved, launches
     t_ms = float(t_ms.item())
-    total_instances = args.instances * world * args.steps
+    inst_all = args.instances if args.scaling == "strong" else args.instances * world
+    total_instances = inst_all * args.steps
     value = total_instances / (t_ms * 1e-3)
+    inst_stats = st.instances  # per-instance records of the last timed step (objective, rel KKT, iteration counts)
+
+    # ---- strong scaling beside the weak curve: the SAME total of --instances split over the ranks
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        from score_b200.lowering import slice_instances
+
+        n_str = max(1, args.instances // world)
+        g_str = ScoreSolverGroup(slice_instances(prob, 0, n_str), n_streams=args.streams, device=local_rank, n_parts=args.parts)
+        g_str.solve(kkt_tol=KKT_TOL)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            g_str.solve(kkt_tol=KKT_TOL)
+        e1.record()
+        barrier()
+        ts = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        g_str.close()
+        strong = {
+            "instances_total": n_str * world,
+            "instances_per_gpu": n_str,
+            "value": n_str * world * args.steps / (float(ts.item()) * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": float(ts.item()) / args.steps,
+            "how": "every rank solves the first instances_per_gpu instances of its shard (same generator, same sizes): the "
+            "--instances total of the single-GPU run split over the ranks; device-timed, max over ranks",
+        }
 
     # ---- roofline of the dominant kernel
     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -371,7 +493,10 @@ def run_gpu_arm(args, rank, local_rank, world):
             traffic = json.load(open(tpath)).get(KERNEL_NAMES[dom])
         except (OSError, ValueError):
             traffic = None
-    full_ms = stf.kernel_ms / np.maximum(1, stf.kernel_count)
+    # per-launch figures at full occupancy: only launches whose work list is the whole batch (line-search-only kernels
+    # in the line-search tick, all others in the first PCG tick of cycles 2-5) — NOT the mean over every launch of
+    # those cycles, which mixes in the nearly empty evaluation-tick and late-PCG-tick launches
+    full_ms = stf.kernel_ms_full / np.maximum(1, stf.kernel_count_full)
     roofline = {
         "bound": "hbm",
         "kernel": KERNEL_NAMES[dom],
@@ -399,8 +524,51 @@ def run_gpu_arm(args, rank, local_rank, world):
             n: (float(b / (v * 1e-3) / 1e9) if v > 0 and b > 0 else None)
             for n, v, b in zip(KERNEL_NAMES, full_ms, stf.kernel_bytes)
         },
+        "full_occupancy_how": "launches whose work list is the whole batch: line-search-only kernels in the line-search "
+        "tick, every other kernel in the first PCG tick, cycles 2-5 (CUDA events, un-graphed)",
         "whole_solve_gbs": bytes_total / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
+        "mean_active_fraction": float((inst_stats["cg_iters"] + inst_stats["newton_iters"]).mean() / max(1, st.ticks)),
     }
+
+    # ---- parity sample: the CPU leg solved the first instances of this rank's shard with the oracle; compare
+    parity = None
+    if cpu_results is not None:
+        ns = min(len(cpu_results), n_local)
+        f_cpu = np.array([r[2] for r in cpu_results[:ns]])
+        f_gpu = np.array([inst_stats[i]["objective"] for i in range(ns)])
+        gaps = np.abs(f_gpu - f_cpu) / np.maximum(1.0, np.abs(f_cpu))
+        parity = {
+            "n": int(ns),
+            "max_rel_obj_gap": float(gaps.max()),
+            "max_kkt_gpu_self_reported": float(max(inst_stats[i]["rel_kkt"] for i in range(ns))),
+            "max_kkt_cpu_oracle": float(max(r[1] for r in cpu_results[:ns])),
+            "how": "same sweep instances solved by the CPU oracle (cpu_baseline leg) and by the CUDA path in the timed step; "
+            "gap = |f_gpu - f_oracle| / max(1, |f_oracle|)",
+        }
+        nk = max(0, min(args.parity_kkt, ns))
+        if nk:
+            from oracle import score_oracle as so  # checker only: certifies the GPU's point, nothing measured here
+            from score_b200 import generators
+
+            sol = solver.solution()
+            worst = 0.0
+            for i in range(nk):
+                fg = generators.manhattan_2d(generators.MC_BASE_SEED + args.first_instance + lo + i, n_robots=args.robots,
+                                             n_steps=args.poses)
+                op = so.assemble(fg, so.QCQP)
+                a, b = prob.pose_off[i], prob.pose_off[i + 1]
+                x = np.zeros(op.n_cols)
+                blk = op.dim * (op.dim + 1)
+                x[: op.P * blk] = sol[0][a:b].ravel()
+                x[op.P * blk : op.P * blk + op.L * op.dim] = sol[2][prob.lm_off[i] : prob.lm_off[i + 1]].ravel()
+                x[op.dist_col0 :] = sol[3][prob.rng_off[i] : prob.rng_off[i + 1]].ravel()
+                worst = max(worst, float(so.kkt_qcqp(op, x)["rel_kkt"]))
+            parity["max_kkt_gpu_oracle_evaluated"] = worst
+            parity["n_kkt"] = nk
+
+    # ---- per-config time-to-solve (first half of BASELINE.json's metric): single graphs, one at a time
+    if rank == 0 and world == 1 and not args.no_per_config:
+        per_config = run_per_config(per_config_inputs, local_rank)
 
     # ---- e2e: the same step through the public API with HOST buffers every step:
     # score_create (H2D of the lowered arrays from pinned memory) + score_solve + score_get_solution (D2H) + destroy
@@ -433,7 +601,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             dist.barrier()
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {
-            "value": args.instances * world * n_e2e / float(dt.item()),
+            "value": inst_all * n_e2e / float(dt.item()),
             "unit": UNIT,
             "h2d_bytes_per_step": int(h2d) * world,
             "d2h_bytes_per_step": int(d2h) * world,
@@ -447,6 +615,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "steps; host wall clock over all steps, max over ranks",
         }
 
+    solver.close()  # idempotent
     if rank == 0:
         line = {
             "metric": METRIC,
@@ -457,12 +626,15 @@ def run_gpu_arm(args, rank, local_rank, world):
             "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(args),
             "clocks": clocks,
+            "parity": parity,
+            "per_config": per_config,
+            "strong_scaling": strong,
             "e2e": e2e,
             "gpu_launches": launches_all,
             "roofline": roofline,

@@ -142,6 +142,11 @@ typedef struct {
   double kernel_bytes[12];
   /* algorithmic bytes of each tick kernel summed over the whole solve (per-instance iteration counts) */
   double kernel_bytes_total[12];
+  /* profile mode: the subset of kernel_ms / kernel_count whose work list is the whole batch while every instance is
+   * still running — line-search-only kernels in the line-search tick, all others in the first PCG tick of a cycle
+   * (meaningful when the profiled cycles are early ones) */
+  double kernel_ms_full[12];
+  int64_t kernel_count_full[12];
 } ScoreStats;
 
 typedef struct ScoreHandle_ *ScoreHandle;
@@ -182,8 +187,10 @@ int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, const char *id
  * `capacity` doubles; *count receives the number of doubles the array has; pass out = NULL to query):
  *   SCORE_INT_COARSE_INV  nc x nc inverse coarse matrix of the last Newton step (0 doubles: coarse level off)
  *   SCORE_INT_RANGE_CURV  K_inst x d(d+1)/2 curvature blocks 2 w H_k of the range terms (upper, row-major)
- *   SCORE_INT_FRAMES      P_inst x d x (d+1) dead-reckoned frames of the odometry-chain preconditioner */
-enum { SCORE_INT_COARSE_INV = 0, SCORE_INT_RANGE_CURV = 1, SCORE_INT_FRAMES = 2 };
+ *   SCORE_INT_FRAMES      P_inst x d x (d+1) dead-reckoned frames of the odometry-chain preconditioner
+ *   SCORE_INT_TRACE       (only after a solve with ScoreParams.verbose >= 2) 256 x 8 doubles, one record per Newton
+ *                         step: barrier parameter, step length, PCG iterations, decrement^2, F_mu, r.s, ladder shift, eta */
+enum { SCORE_INT_COARSE_INV = 0, SCORE_INT_RANGE_CURV = 1, SCORE_INT_FRAMES = 2, SCORE_INT_TRACE = 3 };
 int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, double *out, int64_t capacity, int64_t *count);
 
 /* Stand-alone SO(d) rounding of n d x d matrices (host pointers) on the device:

@@ -279,6 +279,7 @@ def solve_qcqp_barrier(
     newton_tol: float = 1e-9,
     max_newton: int = 400,
     verbose: bool = False,
+    stop_kkt: Optional[float] = None,
 ) -> OracleSolution:
     """min f(x) s.t. ||delta_k|| <= 1, pin — add_distance_constraints QCQP branch
     (score/utils/gurobi_utils.py:341-344) + objective (:358-377)."""
@@ -369,6 +370,12 @@ def solve_qcqp_barrier(
                 break
         if mu <= mu_final:
             break
+        if stop_kkt is not None and mu <= 1e-6:
+            # certificate-driven stop (bench.py's CPU arm): end the path as soon as the polished point certifies
+            xc = x_pin.copy()
+            xc[free_idx] = x
+            if kkt_qcqp(prob, polish_distances(prob, xc))["rel_kkt"] <= stop_kkt:
+                break
         mu *= 0.1
     xf = x_pin.copy()
     xf[free_idx] = x

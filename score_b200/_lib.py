@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libscore_b200.so")
 
 SCORE_RELAX_QCQP, SCORE_RELAX_SOCP = 0, 1
 SCORE_CSR_FULL, SCORE_CSR_REDUCED, SCORE_CSR_REDUCED_T = 0, 1, 2
-SCORE_INT_COARSE_INV, SCORE_INT_RANGE_CURV, SCORE_INT_FRAMES = 0, 1, 2
+SCORE_INT_COARSE_INV, SCORE_INT_RANGE_CURV, SCORE_INT_FRAMES, SCORE_INT_TRACE = 0, 1, 2, 3
 SCORE_OK, SCORE_ERR_INVALID, SCORE_ERR_CUDA, SCORE_ERR_STATE, SCORE_ERR_ALLOC = 0, -1, -2, -3, -4
 
 _i32p = C.POINTER(C.c_int32)
@@ -115,6 +115,8 @@ class ScoreStats(C.Structure):
         ("profiled_cycles", C.c_int64),
         ("kernel_bytes", C.c_double * 12),
         ("kernel_bytes_total", C.c_double * 12),
+        ("kernel_ms_full", C.c_double * 12),
+        ("kernel_count_full", C.c_int64 * 12),
     ]
 
 

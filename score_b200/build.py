@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscore_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "assemble.cuh", "precond.cuh", "coarse.cuh", "solver.cuh", "extract.cuh", "../../include/score_b200.h"]
+HEADERS = ["common.cuh", "assemble.cuh", "precond.cuh", "coarse.cuh", "dense.cuh", "solver.cuh", "extract.cuh", "evaluate.cuh",
+           "../../include/score_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = OUT + f".tmp{os.getpid()}"
             cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-                   + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp, "-lcusolver", "-lcublas", "-ldl"])
+                   + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp, "-ldl"])
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 sys.stderr.write(res.stdout + res.stderr)

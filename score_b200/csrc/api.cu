@@ -1,5 +1,4 @@
 // libscore_b200 — C ABI (include/score_b200.h) over the sm_100a kernels.
-#include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <math.h>
@@ -17,6 +16,7 @@
 #include "assemble.cuh"
 #include "coarse.cuh"
 #include "common.cuh"
+#include "dense.cuh"
 #include "evaluate.cuh"
 #include "extract.cuh"
 #include "precond.cuh"
@@ -68,6 +68,7 @@ struct ScoreHandle_ {
   int *h_ndone = nullptr;  // pinned, two slots (double-buffered completion count)
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
   std::map<int, cudaGraphExec_t> graphs;  // cycle length (PCG ticks) -> instantiated cycle graph
+  std::map<int, int> graph_kernels;       // cycle length -> kernels in that graph
   double *wsum = nullptr;
   int *nnz_row = nullptr;
   // transpose scratch
@@ -88,15 +89,17 @@ struct ScoreHandle_ {
   double *ls_recv = nullptr, *mk_recv = nullptr;
   size_t red_count = 0;
   SolverVecs Vg{};  // V with the reduced (global) partial sums / curvature blocks / h
-  bool c_big = false;  // single instance with kCoarseMax < nc <= kCoarseBigMax: dense global-memory coarse level
-  cusolverDnHandle_t cusolver = nullptr;
-  double *cs_work = nullptr;
-  int cs_lwork = 0;
-  int *cs_info = nullptr;
+  // instances with kCoarseMax < nc <= kCoarseBigMax: dense global-memory coarse level (dense.cuh); a handle that is
+  // one such instance (c_big) launches its cycles directly and lets the host decide when the level is rebuilt
+  std::vector<int> big;
+  bool c_big = false;
+  double *cb_work = nullptr, *cb_W = nullptr, *cb_raw = nullptr, *cb_scl = nullptr;  // sweep work matrix / panels
+  int cb_ldp = 0;
   std::vector<std::pair<void *, size_t>> allocs;  // arena chunks (ResourceCache)
   char *arena_ptr = nullptr;
   size_t arena_left = 0, arena_hint = 1u << 20;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t last_stream = nullptr;  // stream of the latest score_solve (a caller's stream, or own_stream)
   SolverCfg graph_cfg{};
   bool solved_once = false;
   int dist_per = 0;
@@ -130,29 +133,85 @@ struct ResourceCache {
       if (best >= 0 && c[best].second <= 2 * need + (1u << 20)) {
         *ptr = c[best].first;
         *size = c[best].second;
+        cached_bytes[dev & 15] -= c[best].second;
         c.erase(c.begin() + best);
         return cudaSuccess;
       }
     }
     *size = need;
-    cudaError_t e = cudaMallocAsync(ptr, *size, (cudaStream_t)0);
+    cudaMemPool_t mp = nullptr;
+    cudaError_t e = pool(dev, &mp);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocFromPoolAsync(ptr, *size, mp, (cudaStream_t)0);
     if (e == cudaErrorMemoryAllocation) {
-      // out of memory while chunks of other sizes sit unused in the cache: give those back and try once more
+      // out of memory while chunks of other sizes sit unused in the cache: give those back to the driver and retry
       cudaGetLastError();
       {
         std::lock_guard<std::mutex> lk(mu);
         for (auto &c : chunks[dev & 15]) cudaFreeAsync(c.first, (cudaStream_t)0);
         chunks[dev & 15].clear();
+        cached_bytes[dev & 15] = 0;
       }
       cudaStreamSynchronize((cudaStream_t)0);
-      e = cudaMallocAsync(ptr, *size, (cudaStream_t)0);
+      cudaMemPoolTrimTo(mp, 0);
+      e = cudaMallocFromPoolAsync(ptr, *size, mp, (cudaStream_t)0);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);  // usable on any stream from here on
     return e;
   }
+  // Unused chunks are kept up to kCacheCap bytes per device; beyond that the largest ones go back to the driver
+  // (sweeps over varying problem sizes would otherwise pile up chunks no later handle fits).
   void put_chunk(int dev, void *ptr, size_t size) {
+    std::vector<std::pair<void *, size_t>> evict;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &c = chunks[dev & 15];
+      c.emplace_back(ptr, size);
+      cached_bytes[dev & 15] += size;
+      while (cached_bytes[dev & 15] > cache_cap() && !c.empty()) {
+        int big = 0;
+        for (int i = 1; i < (int)c.size(); ++i)
+          if (c[i].second > c[big].second) big = i;
+        evict.push_back(c[big]);
+        cached_bytes[dev & 15] -= c[big].second;
+        c.erase(c.begin() + big);
+      }
+    }
+    if (!evict.empty()) {
+      for (auto &c : evict) cudaFreeAsync(c.first, (cudaStream_t)0);
+      cudaMemPool_t mp = nullptr;
+      if (pool(dev, &mp) == cudaSuccess) {
+        cudaStreamSynchronize((cudaStream_t)0);
+        cudaMemPoolTrimTo(mp, 0);
+      }
+    }
+  }
+  static size_t cache_cap() {
+    static const size_t cap = getenv("SCORE_CACHE_CAP_MB") ? (size_t)atoll(getenv("SCORE_CACHE_CAP_MB")) << 20 : (size_t)48 << 30;
+    return cap;
+  }
+  // The library's own memory pool (the process's default pool is left alone): freed blocks stay in it, so that
+  // create/destroy cycles of similar problems cost no driver allocation; release_all / eviction trim it.
+  cudaMemPool_t pools[16] = {};
+  size_t cached_bytes[16] = {};
+  cudaError_t pool(int dev, cudaMemPool_t *out) {
     std::lock_guard<std::mutex> lk(mu);
-    chunks[dev & 15].emplace_back(ptr, size);
+    if (!pools[dev & 15]) {
+      cudaMemPoolProps props{};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      cudaError_t e = cudaMemPoolCreate(&pools[dev & 15], &props);
+      if (e != cudaSuccess) {
+        pools[dev & 15] = nullptr;
+        return e;
+      }
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pools[dev & 15], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *out = pools[dev & 15];
+    return cudaSuccess;
   }
   cudaError_t get_stream(int dev, cudaStream_t *st) {
     {
@@ -186,6 +245,24 @@ struct ResourceCache {
     std::lock_guard<std::mutex> lk(mu);
     events[dev & 15].push_back(ev);
   }
+  // events with timing (phase times of score_solve, kernel profile)
+  std::vector<cudaEvent_t> tevents[16];
+  cudaError_t get_tevent(int dev, cudaEvent_t *ev) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &v = tevents[dev & 15];
+      if (!v.empty()) {
+        *ev = v.back();
+        v.pop_back();
+        return cudaSuccess;
+      }
+    }
+    return cudaEventCreate(ev);
+  }
+  void put_tevent(int dev, cudaEvent_t ev) {
+    std::lock_guard<std::mutex> lk(mu);
+    tevents[dev & 15].push_back(ev);
+  }
   // Instantiated cycle graphs of destroyed handles.  cudaGraphExecDestroy was seen to block for ~0.2 s now and then
   // and to block every other thread's CUDA calls with it (e2e timelines, profiles/), so a sweep does not call it per
   // handle: the executables are parked here and destroyed in bulk once many have piled up, or on release_all.
@@ -207,14 +284,21 @@ struct ResourceCache {
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 16; ++d) {
-      if (chunks[d].empty() && streams[d].empty() && events[d].empty()) continue;
+      if (chunks[d].empty() && streams[d].empty() && events[d].empty() && tevents[d].empty() && !pools[d]) continue;
       cudaSetDevice(d);
       for (auto &c : chunks[d]) cudaFreeAsync(c.first, (cudaStream_t)0);
       for (auto st : streams[d]) cudaStreamDestroy(st);
       for (auto ev : events[d]) cudaEventDestroy(ev);
+      for (auto ev : tevents[d]) cudaEventDestroy(ev);
       chunks[d].clear();
       streams[d].clear();
       events[d].clear();
+      tevents[d].clear();
+      cached_bytes[d] = 0;
+      if (pools[d]) {  // the frees above are stream-ordered: wait for them, then hand the memory back to the driver
+        cudaStreamSynchronize((cudaStream_t)0);
+        cudaMemPoolTrimTo(pools[d], 0);
+      }
     }
     cudaSetDevice(cur);
   }
@@ -350,14 +434,33 @@ extern "C" const char *score_last_error(void) { return g_score_last_error.c_str(
 extern "C" void score_release_cached(void) { g_cache.release_all(); }
 extern "C" const char *score_version(void) { return "score_b200 0.1.0 (sm_100a)"; }
 
+// Device scratch of the stand-alone entry points: freed on every exit path.
+namespace {
+struct DevBuf {
+  void *p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T>
+  T *as() const {
+    return (T *)p;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+}  // namespace
+
 // ---- evaluation after the path: SE(d)-aligned absolute trajectory error, batched (evaluate.cuh) --------------
 namespace {
 // est / gt / off are device pointers; outputs are host pointers (any may be null)
 int ate_launch(int dim, int n_traj, const int *d_off, const double *d_est, long es, int ecs, int ec0, const double *d_gt,
                int align, double *rmse, double *R, double *t, cudaStream_t st) {
-  double *d_out = nullptr;
+  DevBuf out;
   const size_t per = 1 + (size_t)dim * dim + dim;
-  SCORE_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * per * n_traj));
+  SCORE_CUDA_CHECK(out.alloc(sizeof(double) * per * n_traj));
+  double *d_out = out.as<double>();
   double *d_rmse = d_out, *d_R = d_out + n_traj, *d_t = d_R + (size_t)n_traj * dim * dim;
   const int grid = std::min(n_traj, 148 * 8);
   if (dim == 2)
@@ -369,7 +472,6 @@ int ate_launch(int dim, int n_traj, const int *d_off, const double *d_est, long 
   if (e == cudaSuccess && rmse) e = cudaMemcpy(rmse, d_rmse, sizeof(double) * n_traj, cudaMemcpyDefault);
   if (e == cudaSuccess && R) e = cudaMemcpy(R, d_R, sizeof(double) * (size_t)n_traj * dim * dim, cudaMemcpyDefault);
   if (e == cudaSuccess && t) e = cudaMemcpy(t, d_t, sizeof(double) * (size_t)n_traj * dim, cudaMemcpyDefault);
-  cudaFree(d_out);
   SCORE_CUDA_CHECK(e);
   return SCORE_OK;
 }
@@ -402,18 +504,17 @@ extern "C" int score_trajectory_ate(int32_t dim, int32_t n_traj, const int32_t *
     return SCORE_ERR_INVALID;
   }
   SCORE_CUDA_CHECK(cudaSetDevice(device));
-  int *d_off = nullptr;
-  double *d_pts = nullptr;  // [est | gt]
-  SCORE_CUDA_CHECK(cudaMalloc(&d_off, sizeof(int) * (n_traj + 1)));
-  cudaError_t e = cudaMalloc(&d_pts, sizeof(double) * std::max<size_t>(1, 2 * n * dim));
-  if (e == cudaSuccess) e = cudaMemcpy(d_off, traj_off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
+  DevBuf off_buf, pts_buf;  // [est | gt]
+  SCORE_CUDA_CHECK(off_buf.alloc(sizeof(int) * (n_traj + 1)));
+  SCORE_CUDA_CHECK(pts_buf.alloc(sizeof(double) * std::max<size_t>(1, 2 * n * dim)));
+  int *d_off = off_buf.as<int>();
+  double *d_pts = pts_buf.as<double>();
+  cudaError_t e = cudaMemcpy(d_off, traj_off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
   if (e == cudaSuccess && n) e = cudaMemcpy(d_pts, est, sizeof(double) * n * dim, cudaMemcpyDefault);
   if (e == cudaSuccess && n) e = cudaMemcpy(d_pts + n * dim, gt, sizeof(double) * n * dim, cudaMemcpyDefault);
   rc = SCORE_OK;
   if (e == cudaSuccess)
     rc = ate_launch(dim, n_traj, d_off, d_pts, dim, 1, 0, d_pts + n * dim, align, rmse, R, t, nullptr);
-  cudaFree(d_off);
-  cudaFree(d_pts);
   SCORE_CUDA_CHECK(e);
   return rc;
 }
@@ -440,17 +541,16 @@ extern "C" int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj
     return SCORE_ERR_INVALID;
   }
   SCORE_CUDA_CHECK(cudaSetDevice(h->device));
-  int *d_off = nullptr;
-  double *d_gt = nullptr;
-  SCORE_CUDA_CHECK(cudaMalloc(&d_off, sizeof(int) * (n_traj + 1)));
-  cudaError_t e = cudaMalloc(&d_gt, sizeof(double) * std::max<size_t>(1, (size_t)P.P * P.d));
-  if (e == cudaSuccess) e = cudaMemcpy(d_off, off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
+  DevBuf off_buf, gt_buf;
+  SCORE_CUDA_CHECK(off_buf.alloc(sizeof(int) * (n_traj + 1)));
+  SCORE_CUDA_CHECK(gt_buf.alloc(sizeof(double) * std::max<size_t>(1, (size_t)P.P * P.d)));
+  int *d_off = off_buf.as<int>();
+  double *d_gt = gt_buf.as<double>();
+  cudaError_t e = cudaMemcpy(d_off, off, sizeof(int) * (n_traj + 1), cudaMemcpyDefault);
   if (e == cudaSuccess) e = cudaMemcpy(d_gt, gt_pos, sizeof(double) * (size_t)P.P * P.d, cudaMemcpyDefault);
   rc = SCORE_OK;
   if (e == cudaSuccess)
     rc = ate_launch(P.d, n_traj, d_off, h->out_poses, P.blk, P.d + 1, P.d, d_gt, align, rmse, R, t, nullptr);
-  cudaFree(d_off);
-  cudaFree(d_gt);
   SCORE_CUDA_CHECK(e);
   return rc;
 }
@@ -492,8 +592,8 @@ extern "C" void score_destroy(ScoreHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
-  if (h->cusolver) cusolverDnDestroy(h->cusolver);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);  // nothing of this handle is in flight any more
+  if (h->last_stream && h->last_stream != h->own_stream) cudaStreamSynchronize(h->last_stream);
   for (auto &kv : h->graphs) g_cache.retire_graph(kv.second);  // destroyed later, in bulk (see ResourceCache)
   for (auto &e : h->ev_done)
     if (e) g_cache.put_event(h->device, e);
@@ -738,14 +838,6 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   h->device = device;
   // footprint estimate for the first arena chunk: operator in both orientations + sort scratch + solver vectors
   h->arena_hint = (size_t)(40 * nnz + 60 * nz + 40 * m) + (1u << 20);
-  {
-    // keep freed blocks in the pool instead of returning them to the OS: create/destroy cycles of similar
-    // problems (sweeps) then cost no cudaMalloc / cudaFree at all
-    cudaMemPool_t pool;
-    SCORE_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;
-    SCORE_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
   DevProblem &P = h->P;
   P.d = d;
   P.blk = (int)blk;
@@ -813,6 +905,47 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     if (s != P.n_seg) {
       g_score_last_error = "seg_inst is not sorted by instance";
       return SCORE_ERR_INVALID;
+    }
+  }
+  // factor indices are trusted by the assembly / preconditioner kernels: check them here (instance-local pose indices
+  // of every relative-pose factor, the odometry link of every pose, the landmark of every prior)
+  {
+    std::vector<int> ei(P.E), ej(P.E), le(P.P), pl(P.Lp);
+    if (P.E) {
+      SCORE_CUDA_CHECK(fetch_to_host(ei.data(), desc->edge_i, sizeof(int) * P.E));
+      SCORE_CUDA_CHECK(fetch_to_host(ej.data(), desc->edge_j, sizeof(int) * P.E));
+    }
+    SCORE_CUDA_CHECK(fetch_to_host(le.data(), desc->link_edge, sizeof(int) * P.P));
+    if (P.Lp) SCORE_CUDA_CHECK(fetch_to_host(pl.data(), desc->prior_l, sizeof(int) * P.Lp));
+    for (int i = 0; i < NI; ++i) {
+      const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
+      for (int e = h->edge_off[i]; e < h->edge_off[i + 1]; ++e)
+        if (ei[e] < 0 || ei[e] >= Pi || ej[e] < 0 || ej[e] >= Pi || ei[e] == ej[e]) {
+          g_score_last_error = "relative-pose factor " + std::to_string(e) + ": pose index out of range or self-edge";
+          return SCORE_ERR_INVALID;
+        }
+      for (int q = h->prior_off[i]; q < h->prior_off[i + 1]; ++q)
+        if (pl[q] < 0 || pl[q] >= Li) {
+          g_score_last_error = "landmark prior " + std::to_string(q) + ": landmark index out of range";
+          return SCORE_ERR_INVALID;
+        }
+      for (int p = h->pose_off[i]; p < h->pose_off[i + 1]; ++p) {
+        const int e = le[p];
+        if (e == -1) continue;
+        const int pl_ = p - h->pose_off[i];
+        if (e < h->edge_off[i] || e >= h->edge_off[i + 1] || ej[e] != pl_ || ei[e] != pl_ - 1) {
+          g_score_last_error = "link_edge[" + std::to_string(p) + "] is not the odometry factor (p-1 -> p) of its instance";
+          return SCORE_ERR_INVALID;
+        }
+      }
+    }
+    for (int s = 0; s < P.n_seg; ++s) {
+      bool ok = le[seg_ptr[s]] == -1;
+      for (int p = seg_ptr[s] + 1; ok && p < seg_ptr[s + 1]; ++p) ok = le[p] >= 0;
+      if (!ok) {
+        g_score_last_error = "a chain segment must start at a pose without an odometry link and be linked throughout";
+        return SCORE_ERR_INVALID;
+      }
     }
   }
 #define UP(field, src, n)                                   \
@@ -884,9 +1017,15 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
       const int nsegfree = h->seg_begin[i + 1] - h->seg_begin[i] - 1;
       const int nb = nsegfree * (int)blk, nc = nb + (h->lm_off[i + 1] - h->lm_off[i]) * d;
       const bool small = nc > 0 && nc <= kCoarseMax;
-      const bool big = NI == 1 && nc > kCoarseMax && nc <= kCoarseBigMax;
+      const bool big = nc > kCoarseMax && nc <= kCoarseBigMax;
       const bool on = small || big;
-      h->c_big = big;
+      if (big) h->big.push_back(i);
+      if (nc > kCoarseBigMax) {
+        static std::atomic<bool> warned(false);
+        if (!warned.exchange(true))
+          fprintf(stderr, "[score_b200] instance %d: coarse space of %d coordinates exceeds %d; solving it without a coarse "
+                          "level (correct, but PCG converges slowly)\n", i, nc, kCoarseBigMax);
+      }
       h->c_n[i] = on ? nc : 0;
       h->c_nb[i] = on ? nb : 0;
       h->c_off[i + 1] = h->c_off[i] + (on ? nc : 0);
@@ -902,6 +1041,16 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     if ((rc = upload(h, &P.c_moff, h->c_moff.data(), NI + 1))) return rc;
     if ((rc = upload(h, &P.c_n, h->c_n.data(), NI))) return rc;
     if ((rc = upload(h, &P.c_nb, h->c_nb.data(), NI))) return rc;
+    h->c_big = NI == 1 && !h->big.empty();
+    if (!h->big.empty()) {
+      int nbig = 0;
+      for (int i : h->big) nbig = std::max(nbig, h->c_n[i]);
+      h->cb_ldp = (nbig + 7) & ~7;
+      DA(h->cb_work, (size_t)nbig * nbig)
+      DA(h->cb_W, kDB * kDB)
+      DA(h->cb_raw, (size_t)kDB * h->cb_ldp)
+      DA(h->cb_scl, (size_t)kDB * h->cb_ldp)
+    }
     DA(P.c_Ainv, (size_t)moff)
     DA(P.c_rhs, h->c_off[NI])
     DA(P.c_sol, h->c_off[NI])
@@ -1034,30 +1183,44 @@ extern "C" int score_create(const ScoreProblemDesc *desc, int32_t device, ScoreH
 }
 
 
-// Optional per-kernel CUDA-event timing of un-graphed ticks (profile mode).
+// Optional per-kernel CUDA-event timing of un-graphed ticks (profile mode).  Events come from the process-wide
+// cache and go back to it.  Every mark carries the tick it belongs to (tag 0: line-search tick, 1: evaluation
+// tick, 2 + i: i-th PCG tick of the cycle), so that launches whose work list is the whole batch — the line-search
+// tick's line-search-only kernels and the FIRST PCG tick of an early cycle — can be averaged on their own.
 struct TickProfiler {
   std::vector<cudaEvent_t> ev;
-  std::vector<int> ids;
-  cudaStream_t st;
+  std::vector<int> ids, tags;
+  cudaStream_t st = nullptr;
+  int device = 0, tag = 0;
   void mark(int id) {
     cudaEvent_t e;
-    cudaEventCreate(&e);
+    if (g_cache.get_tevent(device, &e) != cudaSuccess) return;
     cudaEventRecord(e, st);
     ev.push_back(e);
     ids.push_back(id);
+    tags.push_back(tag);
   }
   // call after the stream is synchronised
-  void collect(double *ms, long long *count) {
+  void collect(double *ms, long long *count, double *ms_full, long long *count_full) {
     for (size_t i = 0; i + 1 < ev.size(); ++i) {
       if (ids[i] < 0) continue;
       float t = 0.f;
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
       ms[ids[i]] += t;
       count[ids[i]] += 1;
+      const bool ls_only = ids[i] == KI_LINESEARCH || ids[i] == KI_ROWUPDATE || ids[i] == KI_COARSE_BUILD;
+      if ((ls_only && tags[i] == 0) || (!ls_only && tags[i] == 2)) {
+        ms_full[ids[i]] += t;
+        count_full[ids[i]] += 1;
+      }
     }
-    for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : ev) g_cache.put_tevent(device, e);
     ev.clear();
     ids.clear();
+    tags.clear();
+  }
+  ~TickProfiler() {
+    for (auto &e : ev) g_cache.put_tevent(device, e);
   }
 };
 
@@ -1099,26 +1262,19 @@ static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStrea
 #undef SCORE_CB
 }
 
-// Dense coarse level of a large single instance: accumulate into global memory, Cholesky-factorise and invert
-// with cuSOLVER (plain library calls), mirror to a full symmetric matrix.
+// Dense coarse level of a large instance: accumulate into the global-memory work matrix, invert it by blocked
+// symmetric sweeps (dense.cuh; every kernel gated on the instance's phase), symmetrised copy into c_Ainv.
 template <int D>
-static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st) {
+static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, int inst, cudaStream_t st) {
   const DevProblem &P = h->P;
-  const int n = h->c_n[0];
-  double *A = P.c_Ainv;
-  SCORE_CUDA_CHECK(cudaMemsetAsync(A, 0, sizeof(double) * (size_t)n * n, st));
-  k_coarse_big_accum<D><<<h->n_sm * 4, kBigThreads, 0, st>>>(P, h->n_ranks > 1 ? h->Vg : h->V, cfg.coarse_reg, A);
-  k_coarse_big_finish<D><<<grid_for(n, 256), 256, 0, st>>>(P, A);
-  // row-major upper triangle == column-major lower triangle
-  if (cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, A, n, h->cs_work, h->cs_lwork, h->cs_info) !=
-          CUSOLVER_STATUS_SUCCESS ||
-      cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, A, n, h->cs_work, h->cs_lwork, h->cs_info) !=
-          CUSOLVER_STATUS_SUCCESS) {
-    g_score_last_error = "cuSOLVER potrf/potri failed on the coarse matrix";
-    return SCORE_ERR_CUDA;
-  }
-  k_mirror_upper<<<grid_for((long)n * n, 256), 256, 0, st>>>(A, n);
-  return SCORE_OK;
+  const int n = h->c_n[inst];
+  double *A = h->cb_work;
+  cudaMemsetAsync(A, 0, sizeof(double) * (size_t)n * n, st);
+  k_coarse_big_accum<D><<<h->n_sm * 4, kBigThreads, 0, st>>>(P, h->n_ranks > 1 ? h->Vg : h->V, cfg.coarse_reg, A, inst, h->st);
+  k_coarse_big_finish<D><<<grid_for((long)n * n, 256), 256, 0, st>>>(P, A, inst, h->st);
+  const int k = launch_dense_sweep(A, n, n, h->cb_W, h->cb_raw, h->cb_scl, h->cb_ldp, h->st, inst, st);
+  k_dense_finish<<<grid_for((long)n * n, 256), 256, 0, st>>>(A, n, n, P.c_Ainv + h->c_moff[inst], n, h->st, inst);
+  return 3 + k;
 }
 
 static bool coarse_apply_split() {
@@ -1139,14 +1295,17 @@ static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
   if (h->c_nmax > 0 && split) {
     if (pf) pf->mark(KI_COARSE_APPLY);
     k_coarse_apply<D><<<wgrid(h, P.n_inst, 8), kCoarseApplyThreads, 0, st>>>(P, h->V, h->st, h->W);
-  } else if (h->c_big) {
+  }
+  if (!h->big.empty()) {
     if (pf) pf->mark(KI_COARSE_APPLY);
-    k_coarse_big_apply<<<grid_for(h->c_n[0], kBigThreads / 32), kBigThreads, 0, st>>>(P, h->st);
-    k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st);
+    for (int inst : h->big) {
+      k_coarse_big_apply<<<grid_for(h->c_n[inst], kBigThreads / 32), kBigThreads, 0, st>>>(P, h->st, inst);
+      k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st, inst);
+    }
   }
   if (pf) pf->mark(KI_PRECOND_FWD);
   k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W, fuse);
-  return 2 + ((h->c_nmax > 0 && split) ? 1 : 0) + (h->c_big ? 2 : 0);
+  return 2 + ((h->c_nmax > 0 && split) ? 1 : 0) + 2 * (int)h->big.size();
 }
 
 // Row-partitioned solve: sum a buffer over the ranks (out of place; every rank contributes its own rows only).
@@ -1195,17 +1354,18 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   if (pf) pf->mark(KI_ROWUPDATE);
   k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
   n += 4;
-  const bool build = h->c_nmax > 0 || (h->c_big && big_build);
-  if (dist && build && (h->c_big ? big_build : true))  // every rank needs the curvature blocks of all ranges
+  const bool build_big = !h->big.empty() && (!h->c_big || big_build);  // a single large instance: host-decided
+  const bool build = h->c_nmax > 0 || build_big;
+  if (dist && build)  // every rank needs the curvature blocks of all ranges
     dist_allreduce(h, h->V.mk, h->mk_recv, (size_t)P.K * (D * (D + 1) / 2), st);
   if (h->c_nmax > 0) {
     if (pf) pf->mark(KI_COARSE_BUILD);
     launch_coarse_build<D>(h, cfg, st);
     n += 1;
-  } else if (h->c_big && big_build) {
+  }
+  if (build_big) {
     if (pf) pf->mark(KI_COARSE_BUILD);
-    launch_coarse_big_build<D>(h, cfg, st);
-    n += 4;
+    for (int inst : h->big) n += launch_coarse_big_build<D>(h, cfg, inst, st);
   }
   if (pf) pf->mark(KI_COLPASS);
   n += launch_colpass(h, st, TM_LS);
@@ -1278,9 +1438,14 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
 template <int D>
 static int launch_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr,
                         bool big_build = false) {
+  if (pf) pf->tag = 0;
   int n = launch_ls_tick<D>(h, cfg, st, pf, big_build);
+  if (pf) pf->tag = 1;
   n += launch_eval_tick<D>(h, cfg, st, pf);
-  for (int i = 0; i < n_cg; ++i) n += launch_cg_tick<D>(h, cfg, st, i == n_cg - 1, pf);
+  for (int i = 0; i < n_cg; ++i) {
+    if (pf) pf->tag = 2 + i;
+    n += launch_cg_tick<D>(h, cfg, st, i == n_cg - 1, pf);
+  }
   return n;
 }
 static int launch_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr,
@@ -1327,8 +1492,27 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   const int d = P.d;
   long launches = 0;
 
-  cudaEvent_t ev[5];
-  for (auto &e : ev) SCORE_CUDA_CHECK(cudaEventCreate(&e));
+  if (prm.verbose >= 2 && !V.trace) {  // diagnostic per-Newton-step trace (score_get_internal SCORE_INT_TRACE)
+    V.trace_cap = 256;
+    if ((rc = dalloc(h, &V.trace, (size_t)P.n_inst * V.trace_cap * kTraceRec))) return rc;
+    for (auto &kv : h->graphs) g_cache.retire_graph(kv.second);  // captured kernel parameters hold the old V
+    h->graphs.clear();
+  }
+  if (V.trace) SCORE_CUDA_CHECK(cudaMemsetAsync(V.trace, 0, sizeof(double) * (size_t)P.n_inst * V.trace_cap * kTraceRec, st));
+
+  // phase-timing events: from the process-wide cache, returned on every exit path
+  struct PhaseEvents {
+    cudaEvent_t e[5] = {};
+    int dev = 0;
+    ~PhaseEvents() {
+      for (auto x : e)
+        if (x) g_cache.put_tevent(dev, x);
+    }
+  } pev;
+  pev.dev = h->device;
+  cudaEvent_t *ev = pev.e;
+  for (int i = 0; i < 5; ++i) SCORE_CUDA_CHECK(g_cache.get_tevent(h->device, &ev[i]));
+  h->last_stream = st;
   SCORE_CUDA_CHECK(cudaEventRecord(ev[0], st));
 
   // ---- 1. assembly: reduced operator, its transpose
@@ -1369,7 +1553,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     k_build_M<<<grid_for(P.P, 128), 128, 0, st>>>(P, h->wsum);
     k_init_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z);
     k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
-    if ((h->c_nmax > 0 || h->c_big) && std::max(P.c_ninc, P.c_npair) > 0) {
+    if ((h->c_nmax > 0 || !h->big.empty()) && std::max(P.c_ninc, P.c_npair) > 0) {
       if (d == 2)
         k_coarse_static<2><<<grid_for(std::max(P.c_ninc, P.c_npair), 256), 256, 0, st>>>(P);
       else
@@ -1423,13 +1607,21 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       *out = it->second;
       return SCORE_OK;
     }
-    cudaGraph_t graph;
-    cudaGraphExec_t exec;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
     SCORE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    launch_cycle_d(h, cfg, st, n_cg);
-    SCORE_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-    SCORE_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-    cudaGraphDestroy(graph);
+    const int nk = launch_cycle_d(h, cfg, st, n_cg);
+    // a failed launch inside the capture surfaces here; the capture is always ended so the stream stays usable
+    cudaError_t ce = cudaGetLastError();
+    const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+    if (ce == cudaSuccess) ce = ee;
+    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      g_score_last_error = std::string("capturing the solver cycle failed: ") + cudaGetErrorString(ce);
+      return SCORE_ERR_CUDA;
+    }
+    h->graph_kernels[n_cg] = nk;
     h->graphs[n_cg] = exec;
     *out = exec;
     return SCORE_OK;
@@ -1437,35 +1629,19 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 4;
   const int grow_after = prm.cg_grow_after > 0 ? prm.cg_grow_after : (1 << 30);
   const int grow_every = prm.cg_grow_every > 0 ? prm.cg_grow_every : 8;
-  const int n_capply = (h->c_nmax > 0 && coarse_apply_split()) ? 1 : 0;  // stand-alone coarse application kernel
-  const int kernels_per_cg_tick = 7 + n_capply, kernels_per_ls_tick = 10 + (h->c_nmax > 0 ? 1 : 0) + n_capply + 3;
   long ticks = 0, cycles = 0;
-  double kernel_ms[12] = {0};
-  long long kernel_count[12] = {0};
+  double kernel_ms[12] = {0}, kernel_ms_full[12] = {0};
+  long long kernel_count[12] = {0}, kernel_count_full[12] = {0};
   long profiled = 0;
   const int prof_skip = prm.profile_cycles > 0 ? std::max(0, prm.profile_skip) : 0;
   const int prof_end = prm.profile_cycles > 0 ? prof_skip + prm.profile_cycles : 0;
   TickProfiler pf;
   pf.st = st;
+  pf.device = h->device;
   h->h_ndone[0] = h->h_ndone[1] = 0;
   if (h->c_big || h->n_ranks > 1) {
     // large single instance: cuSOLVER / NCCL are not captured into graphs; cycles are launched directly and the host
     // decides per cycle whether the line-search tick will rebuild the coarse level (the instance is in PH_LS)
-    if (h->c_big && !h->cusolver) {
-      if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS) {
-        g_score_last_error = "cusolverDnCreate failed";
-        return SCORE_ERR_CUDA;
-      }
-      const int n = h->c_n[0];
-      int l1 = 0, l2 = 0;
-      cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, P.c_Ainv, n, &l1);
-      cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, n, P.c_Ainv, n, &l2);
-      h->cs_lwork = std::max(l1, l2);
-      if ((rc = dalloc(h, &h->cs_work, (size_t)h->cs_lwork))) return rc;
-      if ((rc = dalloc(h, &h->cs_info, 1))) return rc;
-      SCORE_CUDA_CHECK(cudaDeviceSynchronize());
-    }
-    if (h->c_big) cusolverDnSetStream(h->cusolver, st);
     const int n_cg = cg_base;
     while (ticks < max_ticks) {
       InstState s0;
@@ -1483,14 +1659,14 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     const int n_cg = cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
     const bool prof = cycles >= prof_skip && cycles < prof_end;
     if (prof) {
-      launch_cycle_d(h, cfg, st, n_cg, &pf);
+      launches += launch_cycle_d(h, cfg, st, n_cg, &pf);
       profiled += 1;
     } else {
       cudaGraphExec_t exec;
       if ((rc = cycle_graph(n_cg, &exec))) return rc;
       SCORE_CUDA_CHECK(cudaGraphLaunch(exec, st));
+      launches += h->graph_kernels[n_cg];
     }
-    launches += kernels_per_ls_tick + (long)n_cg * kernels_per_cg_tick;
     ticks += 1 + n_cg;
     const int slot = (int)(cycles & 1);
     SCORE_CUDA_CHECK(cudaMemcpyAsync(&h->h_ndone[slot], h->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1503,11 +1679,11 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     }
     if (prof && cycles == prof_end) {
       SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
-      pf.collect(kernel_ms, kernel_count);
+      pf.collect(kernel_ms, kernel_count, kernel_ms_full, kernel_count_full);
     }
   }
   SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
-  if (!pf.ev.empty()) pf.collect(kernel_ms, kernel_count);
+  if (!pf.ev.empty()) pf.collect(kernel_ms, kernel_count, kernel_ms_full, kernel_count_full);
   SCORE_CUDA_CHECK(cudaEventRecord(ev[3], st));
   // ---- 4. extraction
   k_split_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z, h->out_poses, h->out_lms);
@@ -1579,9 +1755,10 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       stats->kernel_count[k] = kernel_count[k];
       stats->kernel_bytes[k] = kbytes_launch[k];
       stats->kernel_bytes_total[k] = kbytes_total[k];
+      stats->kernel_ms_full[k] = kernel_ms_full[k];
+      stats->kernel_count_full[k] = kernel_count_full[k];
     }
   }
-  for (auto &e : ev) cudaEventDestroy(e);
   return SCORE_OK;
 }
 
@@ -1647,13 +1824,14 @@ extern "C" int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t
     if (n_cols) *n_cols = cols;
     if (nnz) *nnz = nn;
     if (!indptr && !indices && !values && !weights && !rhs) return SCORE_OK;
-    int *dip = nullptr, *dc = nullptr;
-    double *dv = nullptr, *dw = nullptr, *db = nullptr;
-    SCORE_CUDA_CHECK(cudaMalloc(&dip, sizeof(int) * (rows + 1)));
-    SCORE_CUDA_CHECK(cudaMalloc(&dc, sizeof(int) * (nn + 1)));
-    SCORE_CUDA_CHECK(cudaMalloc(&dv, sizeof(double) * (nn + 1)));
-    SCORE_CUDA_CHECK(cudaMalloc(&dw, sizeof(double) * (rows + 1)));
-    SCORE_CUDA_CHECK(cudaMalloc(&db, sizeof(double) * (rows + 1)));
+    DevBuf bip, bc, bv, bw, bb;
+    SCORE_CUDA_CHECK(bip.alloc(sizeof(int) * (rows + 1)));
+    SCORE_CUDA_CHECK(bc.alloc(sizeof(int) * (nn + 1)));
+    SCORE_CUDA_CHECK(bv.alloc(sizeof(double) * (nn + 1)));
+    SCORE_CUDA_CHECK(bw.alloc(sizeof(double) * (rows + 1)));
+    SCORE_CUDA_CHECK(bb.alloc(sizeof(double) * (rows + 1)));
+    int *dip = bip.as<int>(), *dc = bc.as<int>();
+    double *dv = bv.as<double>(), *dw = bw.as<double>(), *db = bb.as<double>();
     AsmOut out{dip, dc, dv, dw, db, nullptr};
     const long nf = (long)Ei + Ki + Lpi;
     k_assemble<<<grid_for(nf, 256), 256, 0, h->own_stream>>>(P, q ? ASM_FULL_QCQP : ASM_FULL_SOCP, inst, inst + 1, out);
@@ -1664,11 +1842,6 @@ extern "C" int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t
     if (values) SCORE_CUDA_CHECK(cudaMemcpy(values, dv, sizeof(double) * nn, cudaMemcpyDefault));
     if (weights) SCORE_CUDA_CHECK(cudaMemcpy(weights, dw, sizeof(double) * rows, cudaMemcpyDefault));
     if (rhs) SCORE_CUDA_CHECK(cudaMemcpy(rhs, db, sizeof(double) * rows, cudaMemcpyDefault));
-    cudaFree(dip);
-    cudaFree(dc);
-    cudaFree(dv);
-    cudaFree(dw);
-    cudaFree(db);
     return SCORE_OK;
   }
   if (which != SCORE_CSR_REDUCED && which != SCORE_CSR_REDUCED_T) {
@@ -1803,6 +1976,10 @@ extern "C" int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, do
       n = (int64_t)(h->pose_off[inst + 1] - h->pose_off[inst]) * P.blk;
       src = P.G + (size_t)h->pose_off[inst] * P.blk;
       break;
+    case SCORE_INT_TRACE:
+      n = h->V.trace ? (int64_t)h->V.trace_cap * kTraceRec : 0;
+      src = h->V.trace ? h->V.trace + (size_t)inst * h->V.trace_cap * kTraceRec : nullptr;
+      break;
     default:
       g_score_last_error = "unknown internal array selector";
       return SCORE_ERR_INVALID;
@@ -1828,15 +2005,14 @@ extern "C" int score_round_so(int32_t dim, int64_t n, const double *mats, double
   }
   if (n == 0) return SCORE_OK;
   SCORE_CUDA_CHECK(cudaSetDevice(device));
-  double *din = nullptr, *dout = nullptr;
+  DevBuf bin, bout;
   const size_t bytes = sizeof(double) * (size_t)n * dim * dim;
-  SCORE_CUDA_CHECK(cudaMalloc(&din, bytes));
-  SCORE_CUDA_CHECK(cudaMalloc(&dout, bytes));
+  SCORE_CUDA_CHECK(bin.alloc(bytes));
+  SCORE_CUDA_CHECK(bout.alloc(bytes));
+  double *din = bin.as<double>(), *dout = bout.as<double>();
   SCORE_CUDA_CHECK(cudaMemcpy(din, mats, bytes, cudaMemcpyDefault));
   k_round_so<<<grid_for(n, 128), 128>>>(dim, n, din, dim * dim, dim, dout);
   SCORE_CUDA_CHECK(cudaGetLastError());
   SCORE_CUDA_CHECK(cudaMemcpy(out, dout, bytes, cudaMemcpyDefault));
-  cudaFree(din);
-  cudaFree(dout);
   return SCORE_OK;
 }

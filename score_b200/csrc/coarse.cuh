@@ -457,7 +457,7 @@ __device__ __forceinline__ void coarse_apply_body(DevProblem P, SolverVecs V, co
   __shared__ double red[NW];
   __shared__ double cs[kCoarseMax], ys[kCoarseMax];
   const int n = P.c_n[inst];
-  if (n <= 0 || st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  if (n <= 0 || n > kCoarseMax || st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
   const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
   const double *c = P.c_rhs + P.c_off[inst];
   double *y = P.c_sol + P.c_off[inst];
@@ -511,52 +511,55 @@ __global__ void __launch_bounds__(kCoarseApplyThreads) k_coarse_apply(DevProblem
   }
 }
 
-// ---- large coarse spaces (kCoarseMax < nc <= kCoarseBigMax, single-instance handles) -------------------------
-// Same sorted-list accumulation, but into a dense nc x nc matrix in global memory; the factorisation /
-// inversion is a plain library call (cuSOLVER potrf + potri, api.cu) and the application a dense mat-vec.
+// ---- large coarse spaces (kCoarseMax < nc <= kCoarseBigMax) -------------------------------------------------
+// Same sorted-list accumulation, but into a dense nc x nc work matrix in global memory, inverted by the blocked
+// symmetric sweeps of dense.cuh; the application is a dense mat-vec (one warp per row).  Every kernel takes the
+// instance it serves, so a batch may hold any number of such instances (launched one after the other).
 
 constexpr int kBigThreads = 256;
 
 template <int D>
-__global__ void __launch_bounds__(kBigThreads) k_coarse_big_accum(DevProblem P, SolverVecs V, double reg, double *A) {
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_accum(DevProblem P, SolverVecs V, double reg, double *A, int inst,
+                                                                  const InstState *st) {
   __shared__ double stage[(kBigThreads / 32) * CoarseDims<D>::STAGE];
+  if (st[inst].phase != PH_LS || st[inst].eval_now) return;
   const int wid = threadIdx.x >> 5;
   const int gw = blockIdx.x * (kBigThreads / 32) + wid, nw = gridDim.x * (kBigThreads / 32);
-  coarse_accumulate<D>(P, V, 0, reg, A, P.c_n[0], gw, nw, false, stage + wid * CoarseDims<D>::STAGE);
+  coarse_accumulate<D>(P, V, inst, reg, A, P.c_n[inst], gw, nw, false, stage + wid * CoarseDims<D>::STAGE);
 }
 
-// priors on the landmark diagonals, identity for coordinates without curvature
+// priors on the landmark diagonals, identity for coordinates without curvature, lower triangle mirrored from the
+// upper one (the accumulation fills the diagonal blocks and the upper off-diagonal blocks)
 template <int D>
-__global__ void k_coarse_big_finish(DevProblem P, double *A) {
-  const int n = P.c_n[0], nb = P.c_nb[0];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double v = A[(size_t)i * n + i];
-  if (i >= nb) {
-    const int q = (i - nb) / D;
-    for (int pl = P.prior_off[0]; pl < P.prior_off[1]; ++pl)
-      if (P.prior_l[pl] == q) v += 2.0 * P.prior_w[pl];
-  }
-  if (!(v > 0.0)) v = 1.0;
-  A[(size_t)i * n + i] = v;
-}
-
-// potri leaves the inverse in one triangle (row-major upper = column-major lower): mirror it
-__global__ void k_mirror_upper(double *A, int n) {
+__global__ void __launch_bounds__(256) k_coarse_big_finish(DevProblem P, double *A, int inst, const InstState *st) {
+  if (st[inst].phase != PH_LS || st[inst].eval_now) return;
+  const int n = P.c_n[inst], nb = P.c_nb[inst];
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * n) return;
   const int i = (int)(t / n), j = (int)(t % n);
-  if (i > j) A[t] = A[(size_t)j * n + i];
+  if (i == j) {
+    double v = A[t];
+    if (i >= nb) {
+      const int q = (i - nb) / D;
+      for (int pl = P.prior_off[inst]; pl < P.prior_off[inst + 1]; ++pl)
+        if (P.prior_l[pl] == q) v += 2.0 * P.prior_w[pl];
+    }
+    if (!(v > 0.0)) v = 1.0;
+    A[t] = v;
+  } else if (i > j) {
+    const int bi = (i < nb) ? i / (D * (D + 1)) : nb + (i - nb) / D, bj = (j < nb) ? j / (D * (D + 1)) : nb + (j - nb) / D;
+    if (bi != bj) A[t] = A[(size_t)j * n + i];  // off-diagonal blocks exist in the upper triangle only
+  }
 }
 
 // y = A_c^-1 c : one warp per row
-__global__ void __launch_bounds__(kBigThreads) k_coarse_big_apply(DevProblem P, const InstState *st) {
-  if (st[0].phase == PH_DONE || st[0].phase == PH_WAIT || st[0].eval_now) return;
-  const int n = P.c_n[0], lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_apply(DevProblem P, const InstState *st, int inst) {
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  const int n = P.c_n[inst], lane = threadIdx.x & 31;
   const int row = blockIdx.x * (kBigThreads / 32) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const double *__restrict__ a = P.c_Ainv + (size_t)row * n;
-  const double *__restrict__ c = P.c_rhs;
+  const double *__restrict__ a = P.c_Ainv + P.c_moff[inst] + (size_t)row * n;
+  const double *__restrict__ c = P.c_rhs + P.c_off[inst];
   double acc0 = 0.0, acc1 = 0.0;
   int j = lane;
   for (; j + 32 < n; j += 64) {
@@ -565,22 +568,23 @@ __global__ void __launch_bounds__(kBigThreads) k_coarse_big_apply(DevProblem P, 
   }
   if (j < n) acc0 += __ldg(a + j) * c[j];
   const double tot = warp_sum(acc0 + acc1);
-  if (lane == 0) P.c_sol[row] = tot;
+  if (lane == 0) P.c_sol[P.c_off[inst] + row] = tot;
 }
 
 // scatter: segment bases -> ytmp, landmarks -> s, partial r.s of the landmark block
 template <int D>
-__global__ void __launch_bounds__(kBigThreads) k_coarse_big_scatter(DevProblem P, SolverVecs V, const InstState *st) {
+__global__ void __launch_bounds__(kBigThreads) k_coarse_big_scatter(DevProblem P, SolverVecs V, const InstState *st, int inst) {
   constexpr int BLK = D * (D + 1);
   __shared__ double red[kBigThreads / 32];
-  if (st[0].phase == PH_DONE || st[0].phase == PH_WAIT || st[0].eval_now) return;
-  const int n = P.c_n[0], nb = P.c_nb[0];
-  const double *y = P.c_sol;
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  const int n = P.c_n[inst], nb = P.c_nb[inst];
+  const double *y = P.c_sol + P.c_off[inst];
+  const int seg0 = P.seg_begin[inst];
   for (int i = threadIdx.x; i < nb; i += kBigThreads) {
-    const int pg = P.seg_ptr[1 + i / BLK];  // base pose of free segment i / BLK
-    V.ytmp[(size_t)pg * BLK + (i % BLK)] = y[i];
+    const int pg = P.seg_ptr[seg0 + 1 + i / BLK];  // base pose of free segment i / BLK
+    V.ytmp[(size_t)P.zoff[inst] + (size_t)(pg - P.pose_off[inst]) * BLK + (i % BLK)] = y[i];
   }
-  const int c0 = P.P * BLK;
+  const int c0 = P.zoff[inst] + (P.pose_off[inst + 1] - P.pose_off[inst]) * BLK;
   double acc = 0.0;
   for (int j = threadIdx.x; j < n - nb; j += kBigThreads) {
     const double sv = y[nb + j];
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(kBigThreads) k_coarse_big_scatter(DevProblem P
     acc += sv * V.r[c0 + j];
   }
   const double tot = block_sum<kBigThreads>(acc, red);
-  if (threadIdx.x == 0) V.part_lm[0] = tot;
+  if (threadIdx.x == 0) V.part_lm[inst] = tot;
 }
 
 }  // namespace score

@@ -104,7 +104,11 @@ struct SolverVecs {
   double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2
   double *part_seg;  // [n_seg] r.s over chain segments
   double *part_lm;   // [n_inst] r.s over landmarks
+  // diagnostic trace (ScoreParams.verbose >= 2): per instance kTraceRec doubles per Newton step, trace_cap steps
+  double *trace;
+  int trace_cap;
 };
+constexpr int kTraceRec = 8;
 
 struct BlockTables {
   BlockDesc *rb, *cb;

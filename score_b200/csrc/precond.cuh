@@ -356,7 +356,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
   const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
   const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
   const int sl = s - P.seg_begin[inst];
-  const int nco = fuse ? P.c_n[inst] : 0;
+  const int nco = (fuse && P.c_n[inst] <= kCoarseMax) ? P.c_n[inst] : 0;  // larger coarse spaces: kernels of their own
   if (nco > 0) {
     const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
     const double *__restrict__ cv = P.c_rhs + P.c_off[inst];

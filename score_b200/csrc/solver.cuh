@@ -639,6 +639,17 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
   if (lane != 0) return;
   rs_new += V.part_lm[inst];
   S.Fmu = Fmu;
+  if (V.trace && S.newton_it < V.trace_cap) {  // one record per Newton step: what the step that just ended looked like
+    double *t = V.trace + ((size_t)inst * V.trace_cap + S.newton_it) * kTraceRec;
+    t[0] = S.mu_ls;
+    t[1] = S.step;
+    t[2] = (double)S.cg_it;
+    t[3] = S.dec;
+    t[4] = Fmu;
+    t[5] = rs_new;
+    t[6] = (double)S.ls_shift;
+    t[7] = S.eta;
+  }
   if (!S.skip_ls) S.newton_it += 1;
   S.skip_ls = 0;
   // start the next Newton solve

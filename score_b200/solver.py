@@ -33,6 +33,8 @@ class SolveStats:
     kernel_count: Optional[np.ndarray] = None  # profile mode: launches of each tick kernel in the profiled cycles
     kernel_bytes_total: Optional[np.ndarray] = None  # algorithmic bytes of each tick kernel over the whole solve
     cycles: int = 0
+    kernel_ms_full: Optional[np.ndarray] = None  # profile mode: launches whose work list is the whole batch
+    kernel_count_full: Optional[np.ndarray] = None
 
 
 KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_coarse_build", "k_colpass", "k_precond_rev",
@@ -149,12 +151,14 @@ class ScoreSolver:
         mu_factor: float = 0.0,
         center_tol: float = 0.0,
         mu_min: float = 0.0,
+        verbose: int = 0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
         prm.max_newton, prm.max_cg, prm.max_ticks = max_newton, max_cg, max_ticks
         prm.kkt_tol, prm.cg_forcing = kkt_tol, cg_forcing
         prm.cg_per_cycle = cg_per_cycle
+        prm.verbose = verbose
         prm.cg_grow_after, prm.cg_grow_every = cg_grow_after, cg_grow_every
         prm.coarse_every = coarse_every
         prm.stream = C.c_void_p(stream) if stream else None
@@ -171,6 +175,8 @@ class ScoreSolver:
             kernel_bytes=np.array(st.kernel_bytes[:len(KERNEL_NAMES)]),
             kernel_count=np.array(st.kernel_count[:len(KERNEL_NAMES)]),
             kernel_bytes_total=np.array(st.kernel_bytes_total[:len(KERNEL_NAMES)]), cycles=int(st.cycles),
+            kernel_ms_full=np.array(st.kernel_ms_full[:len(KERNEL_NAMES)]),
+            kernel_count_full=np.array(st.kernel_count_full[:len(KERNEL_NAMES)]),
         )
         return self.last_stats
 
@@ -300,6 +306,8 @@ class ScoreSolverGroup:
             kernel_ms=sum(s.kernel_ms for s in stats), profiled_cycles=f.profiled_cycles,
             kernel_bytes=sum(s.kernel_bytes for s in stats), kernel_count=sum(s.kernel_count for s in stats),
             kernel_bytes_total=sum(s.kernel_bytes_total for s in stats), cycles=longest("cycles"),
+            kernel_ms_full=sum(s.kernel_ms_full for s in stats) if f.kernel_ms_full is not None else None,
+            kernel_count_full=sum(s.kernel_count_full for s in stats) if f.kernel_count_full is not None else None,
         )
 
     def solve(self, **kw) -> SolveStats:

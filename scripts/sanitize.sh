@@ -1,0 +1,28 @@
+#!/bin/bash
+# compute-sanitizer memcheck + racecheck on a single small graph (man1) and a 7-instance batch.
+# Usage (GPU box): bash scripts/sanitize.sh [out_dir]
+out=${1:-gpurun_out}
+mkdir -p "$out"
+cat > /tmp/sanitize_target.py <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import numpy as np
+from score_b200 import generators
+from score_b200.graph_io import load_graph_npz
+from score_b200.lowering import concat, lower_factor_graph, lower_manhattan_arrays
+from score_b200.solver import ScoreSolver
+fg, _ = load_graph_npz("tests/golden/man1.npz")
+with ScoreSolver(lower_factor_graph(fg)) as s:
+    st = s.solve()
+    print("man1 solved", st.n_solved, "newton", st.instances[0]["newton_iters"], "cg", st.instances[0]["cg_iters"])
+probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=4, n_steps=30)) for i in range(7)]
+with ScoreSolver(concat(probs)) as s:
+    st = s.solve()
+    s.solution()
+    print("batch solved", st.n_solved, "of 7")
+PY
+for tool in memcheck racecheck; do
+  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1
+  echo "$tool exit $?" >> "$out/sanitizer_$tool.log"
+  tail -5 "$out/sanitizer_$tool.log"
+done
