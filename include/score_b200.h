@@ -111,7 +111,11 @@ typedef struct {
   int32_t cg_grow_after;   /* from this cycle on the PCG ticks per cycle double every cg_grow_every cycles, <=0: never */
   int32_t cg_grow_every;   /* <=0: 8                                                 */
   int32_t coarse_every;    /* rebuild the coarse inverse every this many Newton steps of a barrier stage, <=0: 1 */
-  int32_t reserved1;
+  int32_t tail_threshold;  /* > 0: run the fused per-instance PCG kernel (one thread-block cluster per instance) once at
+                              most this many instances are unfinished; <= 0: lockstep ticks only (default) */
+  int32_t operator_mode;   /* PCG operator: 0 matrix-free, factor by factor (default); 1 assembled CSR pair (row pass +
+                              column pass) */
+  int32_t reserved2;
 } ScoreParams;
 
 /* Per-instance result record. */
@@ -134,19 +138,19 @@ typedef struct {
   double algorithmic_bytes;         /* bytes the instances had to move over the whole solve */
   /* profile mode: summed CUDA-event time / launch count of each tick kernel over the profiled cycles; order
    * rowpass, linesearch, ctrl_a, rowupdate, coarse_build, colpass, precond_rev, coarse_apply, precond_fwd,
-   * ctrl_b, pupdate */
-  double kernel_ms[12];
-  int64_t kernel_count[12];
+   * ctrl_b, pupdate, pcg_fused, hessvec */
+  double kernel_ms[16];
+  int64_t kernel_count[16];
   int64_t profiled_cycles;
   /* algorithmic bytes of ONE launch of each tick kernel with every instance active */
-  double kernel_bytes[12];
+  double kernel_bytes[16];
   /* algorithmic bytes of each tick kernel summed over the whole solve (per-instance iteration counts) */
-  double kernel_bytes_total[12];
+  double kernel_bytes_total[16];
   /* profile mode: the subset of kernel_ms / kernel_count whose work list is the whole batch while every instance is
    * still running — line-search-only kernels in the line-search tick, all others in the first PCG tick of a cycle
    * (meaningful when the profiled cycles are early ones) */
-  double kernel_ms_full[12];
-  int64_t kernel_count_full[12];
+  double kernel_ms_full[16];
+  int64_t kernel_count_full[16];
 } ScoreStats;
 
 typedef struct ScoreHandle_ *ScoreHandle;

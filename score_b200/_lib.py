@@ -77,7 +77,9 @@ class ScoreParams(C.Structure):
         ("cg_grow_after", C.c_int32),
         ("cg_grow_every", C.c_int32),
         ("coarse_every", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("tail_threshold", C.c_int32),
+        ("operator_mode", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -110,13 +112,13 @@ class ScoreStats(C.Structure):
         ("rows", C.c_int64),
         ("cols", C.c_int64),
         ("algorithmic_bytes", C.c_double),
-        ("kernel_ms", C.c_double * 12),
-        ("kernel_count", C.c_int64 * 12),
+        ("kernel_ms", C.c_double * 16),
+        ("kernel_count", C.c_int64 * 16),
         ("profiled_cycles", C.c_int64),
-        ("kernel_bytes", C.c_double * 12),
-        ("kernel_bytes_total", C.c_double * 12),
-        ("kernel_ms_full", C.c_double * 12),
-        ("kernel_count_full", C.c_int64 * 12),
+        ("kernel_bytes", C.c_double * 16),
+        ("kernel_bytes_total", C.c_double * 16),
+        ("kernel_ms_full", C.c_double * 16),
+        ("kernel_count_full", C.c_int64 * 16),
     ]
 
 

@@ -19,6 +19,8 @@
 #include "dense.cuh"
 #include "evaluate.cuh"
 #include "extract.cuh"
+#include "fused.cuh"
+#include "hessvec.cuh"
 #include "precond.cuh"
 #include "solver.cuh"
 
@@ -63,6 +65,7 @@ struct ScoreHandle_ {
   WorkLists W{};
   int *wl_mem = nullptr;  // backing store of the work lists
   int n_sm = 148;
+  int n_clusters = 16;  // co-resident clusters of the fused PCG kernel
   InstState *st = nullptr;
   int *d_ndone = nullptr;
   int *h_ndone = nullptr;  // pinned, two slots (double-buffered completion count)
@@ -79,7 +82,9 @@ struct ScoreHandle_ {
   double *out_poses = nullptr, *out_lms = nullptr, *out_round = nullptr, *out_dist = nullptr;
   // host copies of the offset tables
   std::vector<int> pose_off, lm_off, edge_off, rng_off, prior_off, zoff, roff, nnzoff, seg_begin;
-  std::vector<int> rb_begin, cb_begin;
+  std::vector<int> rb_begin, cb_begin, pb_begin;
+  void *inc_tmp = nullptr;  // radix-sort scratch of the incidence lists
+  size_t inc_tmp_bytes = 0;
   std::vector<int> c_off, c_moff, c_n, c_nb;
   int c_nmax = 0;
   // row-partitioned multi-GPU solve of one instance (score_comm_init)
@@ -105,9 +110,10 @@ struct ScoreHandle_ {
   int dist_per = 0;
 };
 
-constexpr int kNumKernels = 11;
+constexpr int kNumKernels = 13;
+constexpr int kStatSlots = 16;  // ScoreStats per-kernel arrays
 enum KernelId { KI_ROWPASS = 0, KI_LINESEARCH, KI_CTRL_A, KI_ROWUPDATE, KI_COARSE_BUILD, KI_COLPASS, KI_PRECOND_REV,
-                KI_COARSE_APPLY, KI_PRECOND_FWD, KI_CTRL_B, KI_PUPDATE };
+                KI_COARSE_APPLY, KI_PRECOND_FWD, KI_CTRL_B, KI_PUPDATE, KI_PCG_FUSED, KI_HESSVEC };
 
 namespace {
 
@@ -392,14 +398,22 @@ int wgrid(const ScoreHandle_ *h, long items, int per_sm) {
 // indices, every array read or written once; DESIGN.md "algorithmic bytes").  Control kernels read a few
 // partial sums and are counted as zero.
 struct InstDims {
-  double d, nnz, m, nz, K, P, nc;
+  double d, nnz, m, nz, K, P, nc, E = 0, L = 0, Lp = 0;
   bool fused = true;  // coarse application inside k_precond_fwd
+  bool mf = false;    // PCG iterations apply the operator matrix-free (k_hessvec)
 };
 double kernel_bytes_inst(int k, int mode, const InstDims &D) {
   const double d = D.d, blk = d * (d + 1), d1 = d + 1, nnz = D.nnz, m = D.m, nz = D.nz, K = D.K, Pn = D.P, nc = D.nc;
   const bool cg = mode == TM_CG, ls = mode == TM_LS, ev = mode == TM_EVAL;
   switch (k) {
+    case KI_HESSVEC: {  // x in, h out, incidence lists, every relative-pose factor once (measurement, 2 precisions, 2 pose
+                        // indices), every range term twice (partner index + curvature block)
+      if (!cg || !D.mf) return 0.0;
+      const double ninc = 2.0 * D.E + 2.0 * K + D.Lp;
+      return 16.0 * nz + 4.0 * (Pn + D.L + 1) + 4.0 * ninc + D.E * (8.0 * (d + d * d + 2) + 8.0) + 2.0 * K * (4.0 + 8.0 * d * (d + 1) / 2);
+    }
     case KI_ROWPASS:  // B (vals+cols+indptr), gather x; CG: w of the plain rows, u out, M_k of the ranges; LS: bdz out
+      if (cg && D.mf) return 0.0;
       if (cg) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * (m - d * K) + 8.0 * m + 8.0 * K * d * (d + 1) / 2;
       if (ls) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * m;
       return 0.0;
@@ -413,6 +427,7 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
       return (ls && nc > 0) ? 2.0 * K * (12.0 + 8.0 * d1 + 4.0 * d * d1) + K * (4.0 + 16.0 * d1 + 4.0 * d * d1) + 8.0 * nc * nc
                             : 0.0;
     case KI_COLPASS:  // B^T, gather u; CG: dz rw, p, r rw; LS: z rw, dz rw, r out; EVAL: z
+      if (cg && D.mf) return 48.0 * nz;  // h, p in; dz, r read + written
       if (cg || ls) return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
       return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * nz;
     case KI_PRECOND_REV:  // r, ytmp out, G, M
@@ -1078,6 +1093,19 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   }
   h->rb_begin[NI] = (int)rb.size();
   h->cb_begin[NI] = (int)cb.size();
+  // pose / landmark blocks of the matrix-free Hessian-vector kernel (instance-local pose / landmark ranges)
+  std::vector<BlockDesc> pb;
+  h->pb_begin.assign(NI + 1, 0);
+  for (int i = 0; i < NI; ++i) {
+    h->pb_begin[i] = (int)pb.size();
+    const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
+    for (int p0 = 0; p0 < Pi; p0 += kPosesPerBlock) pb.push_back({i, p0, std::min(p0 + kPosesPerBlock, Pi), CB_POSE});
+    for (int q0 = 0; q0 < Li; q0 += kLmPerBlock) pb.push_back({i, q0, std::min(q0 + kLmPerBlock, Li), CB_LANDMARK});
+  }
+  h->pb_begin[NI] = (int)pb.size();
+  h->T.n_pb = (int)pb.size();
+  if ((rc = upload(h, &h->T.pb, pb.data(), pb.size()))) return rc;
+  if ((rc = upload(h, &h->T.pb_begin, h->pb_begin.data(), NI + 1))) return rc;
   h->T.n_rb = (int)rb.size();
   h->T.n_cb = (int)cb.size();
   if ((rc = upload(h, &h->T.rb, rb.data(), rb.size()))) return rc;
@@ -1086,8 +1114,9 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   if ((rc = upload(h, &h->T.cb_begin, h->cb_begin.data(), NI + 1))) return rc;
   {
     // work lists: [par, ticket, cnt x6, cnt_ev, pad] + 7 lists of n_inst entries
-    int maxrb = 1, maxcb = 1, maxseg = 1;
+    int maxrb = 1, maxcb = 1, maxseg = 1, maxpb = 1;
     for (int i = 0; i < NI; ++i) {
+      maxpb = std::max(maxpb, h->pb_begin[i + 1] - h->pb_begin[i]);
       maxrb = std::max(maxrb, h->rb_begin[i + 1] - h->rb_begin[i]);
       maxcb = std::max(maxcb, h->cb_begin[i + 1] - h->cb_begin[i]);
       maxseg = std::max(maxseg, h->seg_begin[i + 1] - h->seg_begin[i]);
@@ -1104,9 +1133,11 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     W.maxrb = maxrb;
     W.maxcb = maxcb;
     W.maxseg = maxseg;
+    W.maxpb = maxpb;
     // (cudaGetDeviceProperties fills the whole property struct through the driver and takes milliseconds — far
     // longer when other threads are launching work; one attribute is all that is needed)
     SCORE_CUDA_CHECK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
+    h->n_clusters = std::max(1, h->n_sm / kClusterSize - 2);  // (GPC boundaries leave a few SMs outside any cluster)
   }
   h->red_count = 3 * rb.size() + (size_t)P.nz;
   DA(h->red_send, h->red_count)
@@ -1118,6 +1149,11 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   h->W.rb_lo = 0;
   h->W.rb_hi = (int)rb.size();
   DA(V.part_col, cb.size() * 4)
+  DA(V.h, P.nz)
+  DA(V.part_hv, pb.size())
+  P.n_inc = 2 * P.E + 2 * P.K + P.Lp;
+  DA(P.inc_ptr, (size_t)P.P + P.L + 1)
+  DA(P.inc_code, P.n_inc)
   DA(V.part_seg, P.n_seg)
   DA(V.part_lm, NI)
   DA(h->st, NI)
@@ -1153,6 +1189,25 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     char *tmp = nullptr;
     if ((rc = dalloc(h, &tmp, h->sort_tmp_bytes))) return rc;
     h->sort_tmp = tmp;
+  }
+  if (P.n_inc > 0) {  // the same for the incidence lists of the matrix-free operator (keys: owners)
+    int ob = 1;
+    while ((1ll << ob) <= (long long)P.P + P.L) ++ob;
+    static std::mutex mu;
+    static std::map<std::pair<long long, int>, size_t> known;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair((long long)P.n_inc, ob);
+    auto it = known.find(key);
+    if (it == known.end()) {
+      size_t bytes = 0;
+      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_idx, h->sort_keys, h->sort_perm, P.inc_code,
+                                                       P.n_inc, 0, ob, (cudaStream_t)0));
+      it = known.emplace(key, bytes).first;
+    }
+    h->inc_tmp_bytes = it->second;
+    char *tmp = nullptr;
+    if ((rc = dalloc(h, &tmp, h->inc_tmp_bytes))) return rc;
+    h->inc_tmp = tmp;
   }
   SCORE_CUDA_CHECK(g_cache.get_stream(device, &h->own_stream));
   // the allocations and uploads above are ordered on the default stream; the handle works on its own (non-blocking)
@@ -1342,6 +1397,11 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
   k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  if (h->V.mf) {  // instances still inside a Newton solve take their PCG iteration matrix-free here as well
+    if (pf) pf->mark(KI_HESSVEC);
+    k_hessvec<D><<<wgrid(h, (long)P.n_inst * h->W.maxpb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+    n += 1;
+  }
   if (pf) pf->mark(KI_LINESEARCH);
   k_linesearch<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 3), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (dist) {
@@ -1412,8 +1472,13 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   const bool dist = h->n_ranks > 1;
   const SolverVecs &Vc = dist ? h->Vg : h->V;
   int n = 0;
-  if (pf) pf->mark(KI_ROWPASS);
-  k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  if (h->V.mf) {
+    if (pf) pf->mark(KI_HESSVEC);
+    k_hessvec<D><<<wgrid(h, (long)P.n_inst * h->W.maxpb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  } else {
+    if (pf) pf->mark(KI_ROWPASS);
+    k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  }
   if (dist) {
     if (pf) pf->mark(KI_COLPASS);
     n += launch_colpass(h, st, TM_CG);
@@ -1447,6 +1512,40 @@ static int launch_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, 
     n += launch_cg_tick<D>(h, cfg, st, i == n_cg - 1, pf);
   }
   return n;
+}
+// Tail cycle (few instances left, or a handle that holds few graphs): line-search tick + evaluation tick, then ONE
+// fused kernel in which a thread-block cluster per instance runs the whole PCG solve of the next Newton system
+// (fused.cuh), then the controller files the work lists.  Same per-instance arithmetic as the lockstep cycle.
+template <int D>
+static int launch_tail_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
+  const DevProblem &P = h->P;
+  if (pf) pf->tag = 0;
+  int n = launch_ls_tick<D>(h, cfg, st, pf, false);
+  if (pf) pf->tag = 1;
+  n += launch_eval_tick<D>(h, cfg, st, pf);
+  if (pf) pf->tag = 3;
+  if (pf) pf->mark(KI_PCG_FUSED);
+  const int ncl = std::max(1, std::min(h->n_clusters, P.n_inst));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(ncl * kClusterSize);
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClusterSize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  cudaLaunchKernelEx(&lc, k_pcg_fused<D>, P, h->V, h->T, h->st, cfg, h->d_ndone, h->W, cfg.max_cg + 1);
+  if (pf) pf->mark(KI_CTRL_B);
+  k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_FILE, h->W);
+  if (pf) pf->mark(-1);
+  return n + 2;
+}
+static int launch_tail_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, TickProfiler *pf = nullptr) {
+  return h->P.d == 2 ? launch_tail_cycle<2>(h, cfg, st, pf) : launch_tail_cycle<3>(h, cfg, st, pf);
 }
 static int launch_cycle_d(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st, int n_cg, TickProfiler *pf = nullptr,
                           bool big_build = false) {
@@ -1482,7 +1581,11 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   cfg.mu_eval = 1e-5;
   cfg.coarse_reg = 1e-6;
   cfg.coarse_every = prm.coarse_every > 0 ? prm.coarse_every : 1;
-  cfg.pad = 0;
+  // PCG operator: matrix-free (default) unless the caller asks for the assembled CSR pair, the solve is row-partitioned
+  // over several GPUs (the all-reduce works on the CSR column pass) or the fused per-instance kernel is requested
+  const bool mf = prm.operator_mode == 0 && h->n_ranks == 1 && prm.tail_threshold <= 0;
+  cfg.pad = mf ? 1 : 0;  // part of the graph key: captured kernel parameters carry the mode
+  h->V.mf = mf ? 1 : 0;
   const int max_ticks = prm.max_ticks > 0 ? prm.max_ticks : 200000;
   int rc;
   SCORE_CUDA_CHECK(cudaSetDevice(h->device));
@@ -1539,6 +1642,19 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->sort_keys, h->sort_perm, h->nnz_row + nnz_lo,
                                                             P.vals + nnz_lo, P.t_indptr, P.t_rows, P.t_vals);
     launches += 6;
+    if (P.n_inc > 0) {
+      // incidence lists of the matrix-free operator: (owner, factor) pairs in factor order, stable sort by owner
+      // (the transpose's index scratch is free again)
+      k_inc_fill<<<grid_for((long)P.E + P.K + P.Lp, 256), 256, 0, st>>>(P, h->sort_idx, h->sort_perm);
+      int ob = 1;
+      while ((1ll << ob) <= (long long)P.P + P.L) ++ob;
+      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->inc_tmp, h->inc_tmp_bytes, h->sort_idx, h->sort_keys, h->sort_perm,
+                                                       P.inc_code, P.n_inc, 0, ob, st));
+      k_inc_ptr<<<grid_for(P.n_inc, 256), 256, 0, st>>>(P.n_inc, P.P + P.L, h->sort_keys, P.inc_ptr);
+      launches += 4;
+    } else {
+      SCORE_CUDA_CHECK(cudaMemsetAsync(P.inc_ptr, 0, sizeof(int) * ((size_t)P.P + P.L + 1), st));
+    }
   }
   SCORE_CUDA_CHECK(cudaEventRecord(ev[1], st));
   // ---- 2. preconditioner, start point, solver state
@@ -1610,7 +1726,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     SCORE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int nk = launch_cycle_d(h, cfg, st, n_cg);
+    const int nk = n_cg < 0 ? launch_tail_cycle_d(h, cfg, st) : launch_cycle_d(h, cfg, st, n_cg);
     // a failed launch inside the capture surfaces here; the capture is always ended so the stream stays usable
     cudaError_t ce = cudaGetLastError();
     const cudaError_t ee = cudaStreamEndCapture(st, &graph);
@@ -1629,9 +1745,9 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   const int cg_base = prm.cg_per_cycle > 0 ? prm.cg_per_cycle : 4;
   const int grow_after = prm.cg_grow_after > 0 ? prm.cg_grow_after : (1 << 30);
   const int grow_every = prm.cg_grow_every > 0 ? prm.cg_grow_every : 8;
-  long ticks = 0, cycles = 0;
-  double kernel_ms[12] = {0}, kernel_ms_full[12] = {0};
-  long long kernel_count[12] = {0}, kernel_count_full[12] = {0};
+  long ticks = 0, cycles = 0, tail_cycles = 0;
+  double kernel_ms[kStatSlots] = {0}, kernel_ms_full[kStatSlots] = {0};
+  long long kernel_count[kStatSlots] = {0}, kernel_count_full[kStatSlots] = {0};
   long profiled = 0;
   const int prof_skip = prm.profile_cycles > 0 ? std::max(0, prm.profile_skip) : 0;
   const int prof_end = prm.profile_cycles > 0 ? prof_skip + prm.profile_cycles : 0;
@@ -1655,11 +1771,19 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       cycles += 1;
     }
   }
+  // tail mode (opt-in, ScoreParams.tail_threshold): once at most `tail_thresh` instances are unfinished (known one
+  // cycle late: the completion count is read back asynchronously), cycles run the fused per-instance PCG kernel
+  // instead of lockstep PCG ticks.  Measured (profiles/fused_pcg_r2.txt): bit-identical, but at 8 CTAs per instance an
+  // iteration takes 60-80 us — no faster than a lockstep tick of a nearly empty batch (58 us) — so it is off by default.
+  const int tail_thresh = prm.tail_threshold > 0 ? prm.tail_threshold : -1;
+  const bool tail_ok = h->big.empty() && !coarse_apply_split();
+  int last_done = 0;
   while (!(h->c_big || h->n_ranks > 1) && ticks < max_ticks) {
-    const int n_cg = cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
+    const bool tail = tail_ok && P.n_inst - last_done <= tail_thresh;
+    const int n_cg = tail ? -1 : cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
     const bool prof = cycles >= prof_skip && cycles < prof_end;
     if (prof) {
-      launches += launch_cycle_d(h, cfg, st, n_cg, &pf);
+      launches += tail ? launch_tail_cycle_d(h, cfg, st, &pf) : launch_cycle_d(h, cfg, st, n_cg, &pf);
       profiled += 1;
     } else {
       cudaGraphExec_t exec;
@@ -1667,7 +1791,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       SCORE_CUDA_CHECK(cudaGraphLaunch(exec, st));
       launches += h->graph_kernels[n_cg];
     }
-    ticks += 1 + n_cg;
+    ticks += tail ? 2 : 1 + n_cg;
+    tail_cycles += tail ? 1 : 0;
     const int slot = (int)(cycles & 1);
     SCORE_CUDA_CHECK(cudaMemcpyAsync(&h->h_ndone[slot], h->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
     SCORE_CUDA_CHECK(cudaEventRecord(h->ev_done[slot], st));
@@ -1675,7 +1800,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     // the completion count of the previous cycle is read while this one runs (no host bubble between cycles)
     if (cycles >= 2) {
       SCORE_CUDA_CHECK(cudaEventSynchronize(h->ev_done[slot ^ 1]));
-      if (h->h_ndone[slot ^ 1] >= P.n_inst) break;
+      last_done = h->h_ndone[slot ^ 1];
+      if (last_done >= P.n_inst) break;
     }
     if (prof && cycles == prof_end) {
       SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1698,7 +1824,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   std::vector<InstState> fin(P.n_inst);
   SCORE_CUDA_CHECK(cudaMemcpy(fin.data(), h->st, sizeof(InstState) * P.n_inst, cudaMemcpyDeviceToHost));
   int n_solved = 0;
-  double bytes = 0.0, kbytes_total[12] = {0}, kbytes_launch[12] = {0};
+  double bytes = 0.0, kbytes_total[kStatSlots] = {0}, kbytes_launch[kStatSlots] = {0};
   for (int i = 0; i < P.n_inst; ++i) {
     const InstState &s = fin[i];
     n_solved += (s.phase == PH_DONE && s.solved) ? 1 : 0;
@@ -1710,16 +1836,27 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     D.K = h->rng_off[i + 1] - h->rng_off[i];
     D.P = h->pose_off[i + 1] - h->pose_off[i];
     D.nc = h->c_n[i];
+    D.E = h->edge_off[i + 1] - h->edge_off[i];
+    D.L = h->lm_off[i + 1] - h->lm_off[i];
+    D.Lp = h->prior_off[i + 1] - h->prior_off[i];
+    D.mf = mf;
     D.fused = h->c_nmax > 0 && !coarse_apply_split();
+    double fused_iter = 0.0;  // bytes of one PCG iteration = the PCG-tick bytes of all its kernels
     for (int k = 0; k < kNumKernels; ++k) {
+      if (k == KI_PCG_FUSED) continue;
       const double bcg = kernel_bytes_inst(k, TM_CG, D), bls = kernel_bytes_inst(k, TM_LS, D);
       // the first line-search tick only evaluates the start point (no direction yet)
       const double n_ls = (k == KI_ROWPASS || k == KI_LINESEARCH) ? s.newton_it : s.newton_it + 1.0;
-      const double tot = s.total_cg * bcg + n_ls * bls + s.n_eval * kernel_bytes_inst(k, TM_EVAL, D);
+      // iterations done inside the fused kernel are booked on the fused kernel, not on the stand-alone ones
+      const double tot = (s.total_cg - s.fused_cg) * bcg + n_ls * bls + s.n_eval * kernel_bytes_inst(k, TM_EVAL, D);
       kbytes_total[k] += tot;
       bytes += tot;
       kbytes_launch[k] += (bcg > 0.0) ? bcg : bls;
+      fused_iter += bcg;
     }
+    kbytes_total[KI_PCG_FUSED] += s.fused_cg * fused_iter;
+    bytes += s.fused_cg * fused_iter;
+    kbytes_launch[KI_PCG_FUSED] += fused_iter;
     if (inst_stats) {
       ScoreInstanceStats &o = inst_stats[i];
       o.solved = (s.phase == PH_DONE && s.solved) ? 1 : 0;
@@ -1750,7 +1887,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     stats->cols = P.nz;
     stats->algorithmic_bytes = bytes;
     stats->profiled_cycles = profiled;
-    for (int k = 0; k < 12; ++k) {
+    for (int k = 0; k < kStatSlots; ++k) {
       stats->kernel_ms[k] = kernel_ms[k];
       stats->kernel_count[k] = kernel_count[k];
       stats->kernel_bytes[k] = kbytes_launch[k];

@@ -25,7 +25,7 @@ constexpr int kLsSums = kNumCand + 1 + 3;
 // batch-wide line-search tick of the cycle.
 enum Phase : int { PH_CG = 0, PH_LS = 1, PH_DONE = 2, PH_WAIT = 3 };
 // Tick kind the host schedules (the same for every instance of the batch: the batch advances in lockstep).
-enum TickMode : int { TM_LS = 0, TM_EVAL = 1, TM_CG = 2, TM_CG_LAST = 3 };
+enum TickMode : int { TM_LS = 0, TM_EVAL = 1, TM_CG = 2, TM_CG_LAST = 3, TM_FILE = 4 };
 enum ColKind : int { CB_POSE = 0, CB_LANDMARK = 1 };
 
 // Work descriptor of one CTA of a row-pass / column-pass kernel.  A CTA never
@@ -41,6 +41,7 @@ struct InstState {
   int eval_now, want_eval, n_eval, stall;  // true-KKT evaluation ticks
   double alpha, beta, rs, rs0, eta, step;
   int c_age, ls_shift;                     // Newton steps the current coarse inverse has served; line-search ladder shift
+  int fused_cg, pad0;                      // PCG iterations done inside the fused kernel (fused.cuh)
   double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
@@ -85,6 +86,10 @@ struct DevProblem {
   int *c_orun_off;                   // [n_inst+1] first off-diagonal run of every instance
   int *c_owarp;                      // [n_inst x 33] first off-diagonal run of every warp of the build CTA
   int *c_off, *c_moff, *c_n, *c_nb;  // [n_inst(+1)]
+  // factor incidence lists of the matrix-free Hessian-vector product (hessvec.cuh): owner = global pose index or
+  // P + global landmark index
+  int n_inc;
+  int *inc_ptr, *inc_code;  // [P + L + 1] ; [n_inc]
   double *c_Ainv;                 // per instance nc x nc inverse coarse Hessian
   double *c_rhs, *c_sol;          // coarse right-hand side / solution
 };
@@ -104,6 +109,10 @@ struct SolverVecs {
   double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2
   double *part_seg;  // [n_seg] r.s over chain segments
   double *part_lm;   // [n_inst] r.s over landmarks
+  // matrix-free PCG operator (hessvec.cuh): h = B^T H_r B p and the partial p'Hp of every pose / landmark block
+  double *h;         // [nz]
+  double *part_hv;   // [n_pose_blocks]
+  int mf, pad1;      // 1: PCG iterations apply the operator factor by factor; 0: assembled CSR pair (row + column pass)
   // diagnostic trace (ScoreParams.verbose >= 2): per instance kTraceRec doubles per Newton step, trace_cap steps
   double *trace;
   int trace_cap;
@@ -111,9 +120,9 @@ struct SolverVecs {
 constexpr int kTraceRec = 8;
 
 struct BlockTables {
-  BlockDesc *rb, *cb;
-  int n_rb, n_cb;
-  int *rb_begin, *cb_begin;  // [n_inst+1]
+  BlockDesc *rb, *cb, *pb;  // row blocks, column blocks, pose / landmark blocks of the Hessian-vector kernel
+  int n_rb, n_cb, n_pb;
+  int *rb_begin, *cb_begin, *pb_begin;  // [n_inst+1]
 };
 
 // Compacted lists of the instances a tick has work for, rebuilt on the device by k_ctrl_b at the end of every
@@ -132,7 +141,7 @@ struct WorkLists {
   int *lists;   // [2][3][n_inst] run / ls / wait per parity, then [n_inst] ev   (flat: no dynamic indexing of
   int *ev;      //  kernel-parameter arrays, which would force a local-memory copy of the parameters)
   int n_inst;
-  int maxrb, maxcb, maxseg;  // most row blocks / column blocks / chain segments any instance has
+  int maxrb, maxcb, maxseg, maxpb;  // most row blocks / column blocks / chain segments / pose blocks any instance has
   int rb_lo, rb_hi;          // row blocks this rank owns (row-partitioned multi-GPU solve; [0, n_rb) otherwise)
   __device__ __forceinline__ int *list(int parity, int kind) const { return lists + (size_t)(parity * 3 + kind) * n_inst; }
 };

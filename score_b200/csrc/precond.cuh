@@ -190,8 +190,34 @@ __global__ void k_init_z(DevProblem P, double *z) {
     z[i] = 0.0;
 }
 
+// Barrier of the kSegThreads threads that run a chain-scan body.  SUB = false: they are the whole CTA.  SUB = true:
+// they are the first kSegThreads threads of a larger CTA (the fused PCG kernel, fused.cuh) and meet at named barrier 1.
+template <bool SUB>
+__device__ __forceinline__ void seg_bar() {
+  if (SUB)
+    asm volatile("bar.sync 1, %0;" ::"n"(kSegThreads) : "memory");
+  else
+    __syncthreads();
+}
+
+// block_sum over the kSegThreads scan threads (same tree as block_sum<kSegThreads>)
+template <bool SUB>
+__device__ __forceinline__ double seg_sum(double v, double *smem /* >= kSegThreads/32 */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  seg_bar<SUB>();
+  if (lane == 0) smem[wid] = v;
+  seg_bar<SUB>();
+  double out = 0.0;
+  if (wid == 0) {
+    out = (lane < kSegThreads / 32) ? smem[lane] : 0.0;
+    out = warp_sum(out);
+  }
+  return out;
+}
+
 // Inclusive scan of NV doubles per thread across the CTA (plus running carry across tiles).
-template <int NV>
+template <int NV, bool SUB>
 __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], double *carry) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int NW = kSegThreads / 32;
@@ -207,7 +233,7 @@ __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], do
 #pragma unroll
     for (int c = 0; c < NV; ++c) wtot[wid][c] = v[c];
   }
-  __syncthreads();
+  seg_bar<SUB>();
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
     double add = carry[c];
@@ -219,14 +245,14 @@ __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], do
     ncarry = carry[threadIdx.x];
     for (int w = 0; w < NW; ++w) ncarry += wtot[w][threadIdx.x];
   }
-  __syncthreads();
+  seg_bar<SUB>();
   if (threadIdx.x < NV) carry[threadIdx.x] = ncarry;
 }
 
 // ---- s = P r, pass 1 (reverse): S_p = sum_{q>=p} r_q G_q^T ;  Y_p = S_p M_p -> ytmp.
 // With the coarse level on, the base block S_first goes to the coarse right-hand side instead.
 // CTA per chain segment; CTAs past n_seg handle the landmark block of one instance each.
-template <int D>
+template <int D, bool SUB = false>
 __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, const InstState *st, int s) {
   constexpr int D1 = D + 1, NV = D * D1;
   __shared__ double wtot[kSegThreads / 32][NV];
@@ -251,7 +277,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
       V.s[c0 + j] = sv;
       acc += rv * sv;
     }
-    const double tot = block_sum<kSegThreads>(acc, red);
+    const double tot = seg_sum<SUB>(acc, red);
     if (tid == 0) V.part_lm[inst] = tot;
     return;
   }
@@ -263,7 +289,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
   const bool to_coarse = P.c_n[inst] > 0 && slot >= 0;
 
   if (tid < NV) carry[tid] = 0.0;
-  __syncthreads();
+  seg_bar<SUB>();
   for (int t0 = 0; t0 < len; t0 += kSegThreads) {
     const int idx = t0 + tid;
     const bool valid = idx < len;
@@ -292,7 +318,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
         v[r * D1 + D] = rb[D];
       }
     }
-    cta_scan<NV>(v, wtot, carry);
+    cta_scan<NV, SUB>(v, wtot, carry);
     if (valid) {
       if (pg == p0 && to_coarse) {
         double *c = P.c_rhs + P.c_off[inst] + slot * NV;
@@ -341,7 +367,7 @@ __global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, Solve
 // the CTA of free segment sl needs exactly the blk rows of y that start its prefix sum, the CTA of the pinned
 // first segment takes the landmark rows (-> s, partial r.s).  Every row is one warp's lane-strided dot product,
 // the same summation order as k_coarse_apply, so the two variants agree to the bit.
-template <int D>
+template <int D, bool SUB = false>
 __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s,
                                                  const bool fuse) {
   constexpr int D1 = D + 1, NV = D * D1, NWS = kSegThreads / 32;
@@ -358,8 +384,8 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
   const int sl = s - P.seg_begin[inst];
   const int nco = (fuse && P.c_n[inst] <= kCoarseMax) ? P.c_n[inst] : 0;  // larger coarse spaces: kernels of their own
   if (nco > 0) {
-    const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];
-    const double *__restrict__ cv = P.c_rhs + P.c_off[inst];
+    const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];  // constant during PCG ticks (rebuilt in line-search ticks)
+    const double *cv = P.c_rhs + P.c_off[inst];                  // written by the reverse pass: coherent loads
     const int nb = P.c_nb[inst], lane = tid & 31, wid = tid >> 5;
     const int row0 = (sl >= 1) ? (sl - 1) * NV : nb, nrow = (sl >= 1) ? NV : nco - nb;
     for (int rr = wid; rr < nrow; rr += NWS) {
@@ -371,7 +397,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
     }
   }
   if (tid < NV) carry[tid] = 0.0;
-  __syncthreads();
+  seg_bar<SUB>();
   if (nco > 0 && sl == 0) {  // landmark block: s = y, partial r.s
     const int Pi = P.pose_off[inst + 1] - P.pose_off[inst], c0 = P.zoff[inst] + Pi * NV, nlm = nco - P.c_nb[inst];
     double acc = 0.0;
@@ -380,7 +406,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
       V.s[c0 + j] = sv;
       acc += sv * V.r[c0 + j];
     }
-    const double tot = block_sum<kSegThreads>(acc, red);
+    const double tot = seg_sum<SUB>(acc, red);
     if (tid == 0) V.part_lm[inst] = tot;
   }
   const bool ystart = nco > 0 && sl >= 1;  // the segment's base block starts from the coarse solution
@@ -402,7 +428,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
         for (int c = 0; c < NV; ++c) v[c] = yp[c];
       }
     }
-    cta_scan<NV>(v, wtot, carry);
+    cta_scan<NV, SUB>(v, wtot, carry);
     if (valid) {
       const double *Gp = P.G + (size_t)pg * NV;
       const double *rp = V.r + colbase + (long)pg * NV;
@@ -427,7 +453,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
       }
     }
   }
-  const double tot = block_sum<kSegThreads>(dot, red);
+  const double tot = seg_sum<SUB>(dot, red);
   if (tid == 0) V.part_seg[s] = tot;
 }
 

@@ -141,15 +141,23 @@ __global__ void __launch_bounds__(kThreads) k_residual(DevProblem P, const doubl
 
 // ---- K1: q = B x.  PH_CG: x = p, u = 2 W H_r q (H_r = per-range curvature block tan I + (rad - tan) vv^T/n^2 of
 // F_mu at the current residual, stored as M_k = 2 w H_r by k_rowupdate), partial p'Hp.  PH_LS: x = dz, bdz = q.
-template <int D>
+// NC: gathers of the solver vectors may use the non-coherent path (stand-alone kernels: the vectors are constant for
+// the kernel's lifetime).  The fused PCG kernel (fused.cuh) rewrites them between its phases and needs coherent loads.
+template <bool NC>
+__device__ __forceinline__ double ldv(const double *p) {
+  return NC ? __ldg(p) : *p;
+}
+
+template <int D, bool NC = true>
 __device__ __forceinline__ void rowpass_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
   __shared__ double sq[kRowsPerBlock];
   __shared__ double red[kThreads / 32];
   const BlockDesc bd = T.rb[bid];
   const int phase = st[bd.inst].phase;
   if ((phase != PH_CG && phase != PH_LS) || st[bd.inst].eval_now) return;
+  if (phase == PH_CG && V.mf) return;                 // PCG iterations apply the operator matrix-free (k_hessvec)
   if (phase == PH_LS && st[bd.inst].skip_ls) return;  // start point: no direction yet (bdz stays 0)
-  const double *__restrict__ x = (phase == PH_CG) ? V.p : V.dz;
+  const double *x = (phase == PH_CG) ? V.p : V.dz;
   const int nrows = bd.i1 - bd.i0;
   {
     // rows li = tid + t * kThreads, t < 3 (kRowsPerBlock = 3 kThreads): the index loads of all three rows are
@@ -171,12 +179,12 @@ __device__ __forceinline__ void rowpass_body(DevProblem P, SolverVecs V, BlockTa
 #pragma unroll
       for (int t = 0; t < RPT; ++t) {
         const int k = k0[t] + j;
-        if (k < k1[t]) acc[t] += P.vals[k] * __ldg(x + P.cols[k]);
+        if (k < k1[t]) acc[t] += P.vals[k] * ldv<NC>(x + P.cols[k]);
       }
     }
 #pragma unroll
     for (int t = 0; t < RPT; ++t) {
-      for (int k = k0[t] + 6; k < k1[t]; ++k) acc[t] += P.vals[k] * __ldg(x + P.cols[k]);  // (never taken today)
+      for (int k = k0[t] + 6; k < k1[t]; ++k) acc[t] += P.vals[k] * ldv<NC>(x + P.cols[k]);  // (never taken today)
       const int li = threadIdx.x + t * kThreads;
       if (li < nrows) sq[li] = acc[t];
     }
@@ -336,7 +344,7 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
   if ((phase != PH_CG && phase != PH_LS) || S.eval_now) return;
   const int b0 = T.rb_begin[inst], b1 = T.rb_begin[inst + 1];
   if (phase == PH_CG) {
-    const double pHp = ctrl_sum(V.part_row, b0, b1, 1, 0);
+    const double pHp = V.mf ? ctrl_sum(V.part_hv, T.pb_begin[inst], T.pb_begin[inst + 1], 1, 0) : ctrl_sum(V.part_row, b0, b1, 1, 0);
     if (lane == 0) {
       if (pHp > 0.0 && pHp > 1e-30 * fabs(S.rs) && isfinite(pHp)) {
         S.alpha = S.rs / pHp;
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs
 // `split` (row-partitioned multi-GPU solve): 0 fused; 1 SpMV only (h of this rank's rows -> V.hloc); 2 update only
 // (h read from V.hglob, the sum over the ranks).
 enum ColSplit : int { CS_FUSED = 0, CS_SPMV = 1, CS_APPLY = 2 };
+template <bool NC = true>
 __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
                                                       int mode, int split, const int bid) {
   __shared__ double red[kThreads / 32];
@@ -502,6 +511,11 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
   if (eval ? !st[inst].eval_now : (st[inst].eval_now != 0)) return;
   const double alpha = st[inst].alpha, step = st[inst].step;
   const int pin_end = P.zoff[inst] + P.blk;
+  const double *hsrc = V.hglob;
+  if (V.mf && phase == PH_CG && !eval) {  // h = B^T H_r B p was formed factor by factor (k_hessvec)
+    split = CS_APPLY;
+    hsrc = V.h;
+  }
   double gg = 0.0, gz = 0.0, zz = 0.0;
   auto apply = [&](int col, double h) {
     if (split == CS_SPMV) {
@@ -529,9 +543,9 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
       const int col = bd.i0 + lc;
       double h = 0.0;
       if (split == CS_APPLY) {
-        h = V.hglob[col];
+        h = hsrc[col];
       } else {
-        for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
+        for (int k = P.t_indptr[col]; k < P.t_indptr[col + 1]; ++k) h += P.t_vals[k] * ldv<NC>(V.u + P.t_rows[k]);
       }
       apply(col, h);
     }
@@ -542,10 +556,10 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
       const int col = bd.i0 + lc;
       double h = 0.0;
       if (split == CS_APPLY) {
-        h = V.hglob[col];
+        h = hsrc[col];
       } else {
         for (int k = P.t_indptr[col] + lane; k < P.t_indptr[col + 1]; k += 32)
-          h += P.t_vals[k] * __ldg(V.u + P.t_rows[k]);
+          h += P.t_vals[k] * ldv<NC>(V.u + P.t_rows[k]);
         h = warp_sum(h);
       }
       if (lane == 0) apply(col, h);
@@ -681,7 +695,14 @@ __global__ void __launch_bounds__(kSegThreads) k_ctrl_b(DevProblem P, SolverVecs
   const int n_run = W.cnt[p * 3 + WL_RUN], n_wait = W.cnt[p * 3 + WL_WAIT];
   for (int ai = gw; ai < n_run + n_wait; ai += stride) {
     const int inst = (ai < n_run) ? W.list(p, WL_RUN)[ai] : W.list(p, WL_WAIT)[ai - n_run];
-    if (ai < n_run) {
+    if (mode == TM_FILE) {
+      // after the fused PCG kernel: no bookkeeping left to do, waiting instances take the next line-search tick
+      if (lane == 0 && st[inst].phase == PH_WAIT) {
+        st[inst].phase = PH_LS;
+        st[inst].skip_ls = 0;
+        st[inst].end_cg = 0;
+      }
+    } else if (ai < n_run) {
       ctrl_b_body(P, V, T, st, cfg, n_done, mode, inst);
     } else if (mode == TM_CG_LAST && lane == 0 && st[inst].phase == PH_WAIT) {
       st[inst].phase = PH_LS;

@@ -38,7 +38,7 @@ class SolveStats:
 
 
 KERNEL_NAMES = ["k_rowpass", "k_linesearch", "k_ctrl_a", "k_rowupdate", "k_coarse_build", "k_colpass", "k_precond_rev",
-                "k_coarse_apply", "k_precond_fwd", "k_ctrl_b", "k_pupdate"]
+                "k_coarse_apply", "k_precond_fwd", "k_ctrl_b", "k_pupdate", "k_pcg_fused", "k_hessvec"]
 
 
 _INST_DTYPE = np.dtype(
@@ -152,6 +152,8 @@ class ScoreSolver:
         center_tol: float = 0.0,
         mu_min: float = 0.0,
         verbose: int = 0,
+        tail_threshold: int = 0,
+        operator_mode: int = 0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
@@ -159,6 +161,8 @@ class ScoreSolver:
         prm.kkt_tol, prm.cg_forcing = kkt_tol, cg_forcing
         prm.cg_per_cycle = cg_per_cycle
         prm.verbose = verbose
+        prm.tail_threshold = tail_threshold
+        prm.operator_mode = operator_mode
         prm.cg_grow_after, prm.cg_grow_every = cg_grow_after, cg_grow_every
         prm.coarse_every = coarse_every
         prm.stream = C.c_void_p(stream) if stream else None
