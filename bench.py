@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2, help="sub-batches per GPU solved concurrently on their own streams")
     ap.add_argument("--parts", type=int, default=0, help="sub-batches per GPU (default: --streams); more parts than "
                     "streams staggers them so that one sub-batch's sparse tail runs under the next one's dense start")
+    ap.add_argument("--sets", type=int, default=2, help="handle sets the timed steps are double-buffered over: sets x parts "
+                    "sub-batch solves are in flight (the sparse last cycles of some run under the dense first cycles of others)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --instances per GPU (the default, BASELINE configs[3] per GPU); strong: --instances in total, "
                     "split over the ranks")
@@ -219,9 +221,9 @@ def workload_config(args, sample_note=None):
         "kkt_tol": KKT_TOL,
         "l2": "working set per GPU (~3.5 GB at 1024 instances) is far larger than the 126 MB L2; no explicit flush",
         "parallelism": "independent instances sharded across GPUs, no data-path collective; per GPU the shard is split "
-        f"into {args.parts or args.streams} sub-batches worked through by {args.streams} host threads, each sub-batch on "
-        "its own CUDA stream (staggered starts: the sparse last cycles of one sub-batch run under the dense first cycles "
-        "of the next)",
+        f"into {args.parts or args.streams} sub-batches, each on its own CUDA stream and host thread; the K steps are "
+        "pipelined per sub-batch (no barrier between steps, sub-batches half a solve out of phase: the sparse last cycles "
+        "of one sub-batch run under the dense first cycles of the other); all K steps start and end inside the timed region",
     }
     if sample_note:
         cfg["reference_sample"] = sample_note
@@ -400,8 +402,12 @@ def run_gpu_arm(args, rank, local_rank, world):
     # the batch is split into `--streams` sub-batches, each on its own CUDA stream and host thread
     group = ScoreSolverGroup(prob, n_streams=args.streams, device=local_rank, n_parts=args.parts)
 
-    for _ in range(args.warmup):
-        group.solve(kkt_tol=KKT_TOL)
+    # warm-up and timed region both run the steps as a pipeline (ScoreSolverGroup.solve_steps): every sub-batch is
+    # re-solved step after step by its own host thread, the sub-batches half a solve out of phase, so that the sparse
+    # last cycles of one (a few ill-conditioned instances) run under the dense first cycles of the other.  All K steps
+    # start and finish inside the timed region.
+    group.solve(kkt_tol=KKT_TOL)
+    group.solve_steps(max(args.sets, args.warmup), n_sets=args.sets, kkt_tol=KKT_TOL)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -413,8 +419,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     cycles = 0
     n_solved = 0
     ev0.record()
-    for _ in range(args.steps):
-        st = group.solve(kkt_tol=KKT_TOL)  # returns when every sub-batch stream has drained
+    for st in group.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL):  # returns after the last solve of the last step
         launches += st.kernel_launches
         bytes_total += st.algorithmic_bytes
         solve_ms += st.solve_ms
@@ -451,11 +456,11 @@ def run_gpu_arm(args, rank, local_rank, world):
         n_str = max(1, args.instances // world)
         g_str = ScoreSolverGroup(slice_instances(prob, 0, n_str), n_streams=args.streams, device=local_rank, n_parts=args.parts)
         g_str.solve(kkt_tol=KKT_TOL)
+        g_str.solve_steps(2 * args.sets, n_sets=args.sets, kkt_tol=KKT_TOL)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            g_str.solve(kkt_tol=KKT_TOL)
+        g_str.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL)
         e1.record()
         barrier()
         ts = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -589,11 +594,13 @@ def run_gpu_arm(args, rank, local_rank, world):
         solver.close()
         g2 = ScoreSolverGroup(prob_pinned, n_streams=args.streams, device=local_rank, create=False, n_parts=args.parts)
         g2.prewarm()  # the library's memory / stream caches then hold a spare set of handle resources
-        g2.run_pipelined(out=outs, steps=2, kkt_tol=KKT_TOL)  # same queue depth as the timed run
+        inflight = args.streams * args.sets
+        g2.prewarm(extra=inflight - args.streams)
+        g2.run_pipelined(out=outs, steps=2, inflight=inflight, kkt_tol=KKT_TOL)  # same queue depth as the timed run
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
-        _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, kkt_tol=KKT_TOL)  # returns after the last read-back
+        _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, inflight=inflight, kkt_tol=KKT_TOL)  # returns after the last read-back
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         g2.close()
@@ -608,10 +615,11 @@ def run_gpu_arm(args, rank, local_rank, world):
             "steps": n_e2e,
             "streams": args.streams,
             "parts": args.parts or args.streams,
+            "solves_in_flight": inflight,
             "how": "the `steps` steps are streamed as one queue of sub-batch jobs (`parts` per step); every job does score_create "
             "from pinned host arrays (table build + H2D of its inputs) + score_solve + score_get_solution (D2H of relaxed poses, "
-            "rounded rotations, landmarks, distance variables into pinned host arrays) + score_destroy; `streams` jobs solve "
-            "at a time while one more host thread already runs score_create of the next job; nothing is cached between "
+            "rounded rotations, landmarks, distance variables into pinned host arrays) + score_destroy; `solves_in_flight` jobs "
+            "solve at a time while one more host thread already runs score_create of the next job; nothing is cached between "
             "steps; host wall clock over all steps, max over ranks",
         }
 

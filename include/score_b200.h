@@ -104,9 +104,9 @@ typedef struct {
   int32_t profile_cycles;  /* >0: time every kernel of this many cycles with CUDA events (un-graphed) */
   int32_t profile_skip;    /* cycles to run before the profiled ones                 */
   /* interior-point path following (0: defaults) */
-  double mu0;              /* initial barrier parameter, default 1.0; < 0: no barrier (plain semismooth Newton) */
+  double mu0;              /* initial barrier parameter, default 0.1; < 0: no barrier (plain semismooth Newton) */
   double mu_factor;        /* barrier reduction per centred stage, default 0.1       */
-  double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 4 */
+  double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 16 */
   double mu_min;           /* smallest barrier parameter, default 1e-16              */
   int32_t cg_grow_after;   /* from this cycle on the PCG ticks per cycle double every cg_grow_every cycles, <=0: never */
   int32_t cg_grow_every;   /* <=0: 8                                                 */
@@ -115,7 +115,8 @@ typedef struct {
                               most this many instances are unfinished; <= 0: lockstep ticks only (default) */
   int32_t operator_mode;   /* PCG operator: 0 matrix-free, factor by factor (default); 1 assembled CSR pair (row pass +
                               column pass) */
-  int32_t reserved2;
+  int32_t hi_prio_threshold; /* > 0: the cycles after at most this many instances are left unfinished run on a
+                              high-priority stream (library-owned stream only); <= 0: never (default; measured: no gain) */
 } ScoreParams;
 
 /* Per-instance result record. */

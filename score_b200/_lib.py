@@ -79,7 +79,7 @@ class ScoreParams(C.Structure):
         ("coarse_every", C.c_int32),
         ("tail_threshold", C.c_int32),
         ("operator_mode", C.c_int32),
-        ("reserved2", C.c_int32),
+        ("hi_prio_threshold", C.c_int32),
     ]
 
 

@@ -84,6 +84,7 @@ struct ScoreHandle_ {
   std::vector<int> pose_off, lm_off, edge_off, rng_off, prior_off, zoff, roff, nnzoff, seg_begin;
   std::vector<int> rb_begin, cb_begin, pb_begin;
   void *inc_tmp = nullptr;  // radix-sort scratch of the incidence lists
+  uint4 *inc_in = nullptr;  // unsorted incidence records
   size_t inc_tmp_bytes = 0;
   std::vector<int> c_off, c_moff, c_n, c_nb;
   int c_nmax = 0;
@@ -104,6 +105,8 @@ struct ScoreHandle_ {
   char *arena_ptr = nullptr;
   size_t arena_left = 0, arena_hint = 1u << 20;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t hi_stream = nullptr;   // high-priority twin of own_stream (sparse last cycles)
+  cudaEvent_t ev_switch = nullptr;
   cudaStream_t last_stream = nullptr;  // stream of the latest score_solve (a caller's stream, or own_stream)
   SolverCfg graph_cfg{};
   bool solved_once = false;
@@ -235,6 +238,26 @@ struct ResourceCache {
     std::lock_guard<std::mutex> lk(mu);
     streams[dev & 15].push_back(st);
   }
+  // high-priority streams (the sparse last cycles of a batch, see score_solve)
+  std::vector<cudaStream_t> hi_streams[16];
+  cudaError_t get_hi_stream(int dev, cudaStream_t *st) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto &v = hi_streams[dev & 15];
+      if (!v.empty()) {
+        *st = v.back();
+        v.pop_back();
+        return cudaSuccess;
+      }
+    }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (numerically lower = higher priority)
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
+  }
+  void put_hi_stream(int dev, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(mu);
+    hi_streams[dev & 15].push_back(st);
+  }
   cudaError_t get_event(int dev, cudaEvent_t *ev) {
     {
       std::lock_guard<std::mutex> lk(mu);
@@ -294,6 +317,8 @@ struct ResourceCache {
       cudaSetDevice(d);
       for (auto &c : chunks[d]) cudaFreeAsync(c.first, (cudaStream_t)0);
       for (auto st : streams[d]) cudaStreamDestroy(st);
+      for (auto st : hi_streams[d]) cudaStreamDestroy(st);
+      hi_streams[d].clear();
       for (auto ev : events[d]) cudaEventDestroy(ev);
       for (auto ev : tevents[d]) cudaEventDestroy(ev);
       chunks[d].clear();
@@ -409,8 +434,10 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
     case KI_HESSVEC: {  // x in, h out, incidence lists, every relative-pose factor once (measurement, 2 precisions, 2 pose
                         // indices), every range term twice (partner index + curvature block)
       if (!cg || !D.mf) return 0.0;
-      const double ninc = 2.0 * D.E + 2.0 * K + D.Lp;
-      return 16.0 * nz + 4.0 * (Pn + D.L + 1) + 4.0 * ninc + D.E * (8.0 * (d + d * d + 2) + 8.0) + 2.0 * K * (4.0 + 8.0 * d * (d + 1) / 2);
+      // x in, h out, list bounds, odometry links, 16-byte incidence records of the ranges / priors, every relative-pose
+      // factor once (measurement, 2 precisions), every range term twice (curvature block; the partner gather is in x)
+      return 16.0 * nz + 4.0 * (Pn + D.L + 1) + 4.0 * Pn + 16.0 * (2.0 * K + D.Lp) + D.E * 8.0 * (d + d * d + 2) +
+             2.0 * K * 8.0 * d * (d + 1) / 2;
     }
     case KI_ROWPASS:  // B (vals+cols+indptr), gather x; CG: w of the plain rows, u out, M_k of the ranges; LS: bdz out
       if (cg && D.mf) return 0.0;
@@ -614,6 +641,9 @@ extern "C" void score_destroy(ScoreHandle h) {
     if (e) g_cache.put_event(h->device, e);
   for (auto &c : h->allocs) g_cache.put_chunk(h->device, c.first, c.second);
   if (h->h_ndone && !g_pinned.put(h->h_ndone)) cudaFreeHost(h->h_ndone);
+  if (h->hi_stream) cudaStreamSynchronize(h->hi_stream);
+  if (h->hi_stream) g_cache.put_hi_stream(h->device, h->hi_stream);
+  if (h->ev_switch) g_cache.put_event(h->device, h->ev_switch);
   if (h->own_stream) g_cache.put_stream(h->device, h->own_stream);
   delete h;
 }
@@ -932,13 +962,16 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     }
     SCORE_CUDA_CHECK(fetch_to_host(le.data(), desc->link_edge, sizeof(int) * P.P));
     if (P.Lp) SCORE_CUDA_CHECK(fetch_to_host(pl.data(), desc->prior_l, sizeof(int) * P.Lp));
+    int n_nonlink = 0;
     for (int i = 0; i < NI; ++i) {
       const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
-      for (int e = h->edge_off[i]; e < h->edge_off[i + 1]; ++e)
+      for (int e = h->edge_off[i]; e < h->edge_off[i + 1]; ++e) {
         if (ei[e] < 0 || ei[e] >= Pi || ej[e] < 0 || ej[e] >= Pi || ei[e] == ej[e]) {
           g_score_last_error = "relative-pose factor " + std::to_string(e) + ": pose index out of range or self-edge";
           return SCORE_ERR_INVALID;
         }
+        if (le[h->pose_off[i] + ej[e]] != e) ++n_nonlink;
+      }
       for (int q = h->prior_off[i]; q < h->prior_off[i + 1]; ++q)
         if (pl[q] < 0 || pl[q] >= Li) {
           g_score_last_error = "landmark prior " + std::to_string(q) + ": landmark index out of range";
@@ -954,6 +987,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
         }
       }
     }
+    P.n_nonlink = n_nonlink;
     for (int s = 0; s < P.n_seg; ++s) {
       bool ok = le[seg_ptr[s]] == -1;
       for (int p = seg_ptr[s] + 1; ok && p < seg_ptr[s + 1]; ++p) ok = le[p] >= 0;
@@ -1094,13 +1128,16 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   h->rb_begin[NI] = (int)rb.size();
   h->cb_begin[NI] = (int)cb.size();
   // pose / landmark blocks of the matrix-free Hessian-vector kernel (instance-local pose / landmark ranges)
-  std::vector<BlockDesc> pb;
+  std::vector<HvBlock> pb;
   h->pb_begin.assign(NI + 1, 0);
   for (int i = 0; i < NI; ++i) {
     h->pb_begin[i] = (int)pb.size();
     const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
-    for (int p0 = 0; p0 < Pi; p0 += kPosesPerBlock) pb.push_back({i, p0, std::min(p0 + kPosesPerBlock, Pi), CB_POSE});
-    for (int q0 = 0; q0 < Li; q0 += kLmPerBlock) pb.push_back({i, q0, std::min(q0 + kLmPerBlock, Li), CB_LANDMARK});
+    const int z0 = h->zoff[i], pg0 = h->pose_off[i], lg0 = h->lm_off[i];
+    for (int p0 = 0; p0 < Pi; p0 += kPosesPerBlock)
+      pb.push_back({i, p0, std::min(p0 + kPosesPerBlock, Pi), CB_POSE, z0, pg0, Pi, lg0});
+    for (int q0 = 0; q0 < Li; q0 += kLmPerBlock)
+      pb.push_back({i, q0, std::min(q0 + kLmPerBlock, Li), CB_LANDMARK, z0, pg0, Pi, lg0});
   }
   h->pb_begin[NI] = (int)pb.size();
   h->T.n_pb = (int)pb.size();
@@ -1114,9 +1151,10 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   if ((rc = upload(h, &h->T.cb_begin, h->cb_begin.data(), NI + 1))) return rc;
   {
     // work lists: [par, ticket, cnt x6, cnt_ev, pad] + 7 lists of n_inst entries
-    int maxrb = 1, maxcb = 1, maxseg = 1, maxpb = 1;
+    int maxrb = 1, maxcb = 1, maxseg = 1, maxpb = 1, maxvc = 1;
     for (int i = 0; i < NI; ++i) {
       maxpb = std::max(maxpb, h->pb_begin[i + 1] - h->pb_begin[i]);
+      maxvc = std::max(maxvc, (h->zoff[i + 1] - h->zoff[i] + kVecChunk - 1) / kVecChunk);
       maxrb = std::max(maxrb, h->rb_begin[i + 1] - h->rb_begin[i]);
       maxcb = std::max(maxcb, h->cb_begin[i + 1] - h->cb_begin[i]);
       maxseg = std::max(maxseg, h->seg_begin[i + 1] - h->seg_begin[i]);
@@ -1134,6 +1172,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     W.maxcb = maxcb;
     W.maxseg = maxseg;
     W.maxpb = maxpb;
+    W.maxvc = maxvc;
     // (cudaGetDeviceProperties fills the whole property struct through the driver and takes milliseconds — far
     // longer when other threads are launching work; one attribute is all that is needed)
     SCORE_CUDA_CHECK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -1153,7 +1192,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.part_hv, pb.size())
   P.n_inc = 2 * P.E + 2 * P.K + P.Lp;
   DA(P.inc_ptr, (size_t)P.P + P.L + 1)
-  DA(P.inc_code, P.n_inc)
+  DA(P.inc_rec, P.n_inc)
+  DA(h->inc_in, P.n_inc)
   DA(V.part_seg, P.n_seg)
   DA(V.part_lm, NI)
   DA(h->st, NI)
@@ -1192,7 +1232,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   }
   if (P.n_inc > 0) {  // the same for the incidence lists of the matrix-free operator (keys: owners)
     int ob = 1;
-    while ((1ll << ob) <= (long long)P.P + P.L) ++ob;
+    while ((1ll << ob) <= (long long)P.P + P.L + 1) ++ob;  // owners 0 .. P + L (the last one: the odometry-link sentinel)
     static std::mutex mu;
     static std::map<std::pair<long long, int>, size_t> known;
     std::lock_guard<std::mutex> lk(mu);
@@ -1200,7 +1240,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     auto it = known.find(key);
     if (it == known.end()) {
       size_t bytes = 0;
-      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_idx, h->sort_keys, h->sort_perm, P.inc_code,
+      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_idx, h->sort_keys, h->inc_in, P.inc_rec,
                                                        P.n_inc, 0, ob, (cudaStream_t)0));
       it = known.emplace(key, bytes).first;
     }
@@ -1210,6 +1250,8 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     h->inc_tmp = tmp;
   }
   SCORE_CUDA_CHECK(g_cache.get_stream(device, &h->own_stream));
+  SCORE_CUDA_CHECK(g_cache.get_hi_stream(device, &h->hi_stream));
+  SCORE_CUDA_CHECK(g_cache.get_event(device, &h->ev_switch));
   // the allocations and uploads above are ordered on the default stream; the handle works on its own (non-blocking)
   // stream.  Wait for the default stream only — a device-wide synchronisation would also wait for (and be delayed
   // by) the solves of other handles that are running concurrently.
@@ -1437,7 +1479,7 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   if (pf) pf->mark(KI_CTRL_B);
   k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, TM_LS, h->W);
   if (pf) pf->mark(KI_PUPDATE);
-  k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
+  k_pupdate_vec<<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->st, h->W);
   if (pf) pf->mark(-1);
   return n + 2;
 }
@@ -1488,13 +1530,15 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   if (pf) pf->mark(KI_COLPASS);
   if (dist)
     launch_colapply(h, st, TM_CG);
+  else if (h->V.mf)  // the operator was applied by k_hessvec: what is left of the column pass is element-wise
+    k_cg_update<<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->st, h->W);
   else
     launch_colpass(h, st, TM_CG);
   n += 3 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
   k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG, h->W);
   if (pf) pf->mark(KI_PUPDATE);
-  k_pupdate<<<wgrid(h, (long)P.n_inst * h->W.maxcb, 8), kThreads, 0, st>>>(h->V, h->T, h->st, h->W);
+  k_pupdate_vec<<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->st, h->W);
   if (pf) pf->mark(-1);
   return n + 2;
 }
@@ -1574,9 +1618,9 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   cfg.max_cg = prm.max_cg > 0 ? prm.max_cg : 100;
   cfg.kkt_tol = prm.kkt_tol > 0 ? prm.kkt_tol : 1e-6;
   cfg.forcing = prm.cg_forcing > 0 ? prm.cg_forcing : 0.2;
-  cfg.mu0 = prm.mu0 > 0 ? prm.mu0 : (prm.mu0 < 0 ? 0.0 : 1.0);
+  cfg.mu0 = prm.mu0 > 0 ? prm.mu0 : (prm.mu0 < 0 ? 0.0 : 0.1);
   cfg.mu_factor = (prm.mu_factor > 0 && prm.mu_factor < 1) ? prm.mu_factor : 0.1;
-  cfg.center_tol = prm.center_tol > 0 ? prm.center_tol : 4.0;
+  cfg.center_tol = prm.center_tol > 0 ? prm.center_tol : 16.0;
   cfg.mu_min = prm.mu_min > 0 ? prm.mu_min : 1e-16;
   cfg.mu_eval = 1e-5;
   cfg.coarse_reg = 1e-6;
@@ -1645,11 +1689,11 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     if (P.n_inc > 0) {
       // incidence lists of the matrix-free operator: (owner, factor) pairs in factor order, stable sort by owner
       // (the transpose's index scratch is free again)
-      k_inc_fill<<<grid_for((long)P.E + P.K + P.Lp, 256), 256, 0, st>>>(P, h->sort_idx, h->sort_perm);
+      k_inc_fill<<<grid_for((long)P.E + P.K + P.Lp, 256), 256, 0, st>>>(P, h->sort_idx, h->inc_in);
       int ob = 1;
-      while ((1ll << ob) <= (long long)P.P + P.L) ++ob;
-      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->inc_tmp, h->inc_tmp_bytes, h->sort_idx, h->sort_keys, h->sort_perm,
-                                                       P.inc_code, P.n_inc, 0, ob, st));
+      while ((1ll << ob) <= (long long)P.P + P.L + 1) ++ob;
+      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->inc_tmp, h->inc_tmp_bytes, h->sort_idx, h->sort_keys, h->inc_in,
+                                                       P.inc_rec, P.n_inc, 0, ob, st));
       k_inc_ptr<<<grid_for(P.n_inc, 256), 256, 0, st>>>(P.n_inc, P.P + P.L, h->sort_keys, P.inc_ptr);
       launches += 4;
     } else {
@@ -1717,8 +1761,11 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     h->graphs.clear();
     h->graph_cfg = cfg;
   }
-  auto cycle_graph = [&](int n_cg, cudaGraphExec_t *out) -> int {
-    auto it = h->graphs.find(n_cg);
+  // key: PCG ticks of the cycle (< 0: tail cycle with the fused kernel), + 1000 when captured on the high-priority stream
+  // (kernel nodes keep the priority of the stream they were captured on)
+  auto cycle_graph = [&](int key, cudaGraphExec_t *out) -> int {
+    const int n_cg = key >= 500 ? key - 1000 : key;
+    auto it = h->graphs.find(key);
     if (it != h->graphs.end()) {
       *out = it->second;
       return SCORE_OK;
@@ -1737,8 +1784,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       g_score_last_error = std::string("capturing the solver cycle failed: ") + cudaGetErrorString(ce);
       return SCORE_ERR_CUDA;
     }
-    h->graph_kernels[n_cg] = nk;
-    h->graphs[n_cg] = exec;
+    h->graph_kernels[key] = nk;
+    h->graphs[key] = exec;
     *out = exec;
     return SCORE_OK;
   };
@@ -1778,18 +1825,36 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   const int tail_thresh = prm.tail_threshold > 0 ? prm.tail_threshold : -1;
   const bool tail_ok = h->big.empty() && !coarse_apply_split();
   int last_done = 0;
+  // Sparse last cycles at high stream priority: once at most `hi_thresh` instances are unfinished the batch no longer
+  // fills the GPU and every tick costs the latency of its dependent kernels.  When another handle is solving at the same
+  // time (sub-batches of a sweep on their own streams) those small kernels would queue behind the other handle's large
+  // ones block by block; on the high-priority stream their blocks are dispatched first, so one handle's tail runs UNDER
+  // the other handle's dense cycles instead of being stretched by them.  (Library-owned stream only.)
+  // Measured (profiles/pipeline_probe_r2.txt): no effect — what stretches a tail under another handle's dense cycles is the
+  // loaded memory latency of its dependent loads, not block dispatch order — so it is opt-in.
+  const int hi_thresh = (prm.stream || prm.hi_prio_threshold <= 0) ? -1 : prm.hi_prio_threshold;
+  bool on_hi = false;
   while (!(h->c_big || h->n_ranks > 1) && ticks < max_ticks) {
     const bool tail = tail_ok && P.n_inst - last_done <= tail_thresh;
     const int n_cg = tail ? -1 : cycle_cg_ticks((int)cycles, cg_base, grow_after, grow_every, cfg.max_cg);
+    if (!on_hi && hi_thresh > 0 && cycles >= 2 && P.n_inst - last_done <= hi_thresh && P.n_inst > hi_thresh) {
+      SCORE_CUDA_CHECK(cudaEventRecord(h->ev_switch, st));
+      SCORE_CUDA_CHECK(cudaStreamWaitEvent(h->hi_stream, h->ev_switch, 0));
+      st = h->hi_stream;
+      h->last_stream = st;
+      pf.st = st;
+      on_hi = true;
+    }
     const bool prof = cycles >= prof_skip && cycles < prof_end;
     if (prof) {
       launches += tail ? launch_tail_cycle_d(h, cfg, st, &pf) : launch_cycle_d(h, cfg, st, n_cg, &pf);
       profiled += 1;
     } else {
       cudaGraphExec_t exec;
-      if ((rc = cycle_graph(n_cg, &exec))) return rc;
+      const int key = n_cg + (on_hi ? 1000 : 0);
+      if ((rc = cycle_graph(key, &exec))) return rc;
       SCORE_CUDA_CHECK(cudaGraphLaunch(exec, st));
-      launches += h->graph_kernels[n_cg];
+      launches += h->graph_kernels[key];
     }
     ticks += tail ? 2 : 1 + n_cg;
     tail_cycles += tail ? 1 : 0;

@@ -89,7 +89,9 @@ struct DevProblem {
   // factor incidence lists of the matrix-free Hessian-vector product (hessvec.cuh): owner = global pose index or
   // P + global landmark index
   int n_inc;
-  int *inc_ptr, *inc_code;  // [P + L + 1] ; [n_inc]
+  int *inc_ptr;                  // [P + L + 1]
+  uint4 *inc_rec;                // [n_inc] incidence records (hessvec.cuh)
+  int n_nonlink;                 // relative-pose factors that are not odometry links (loop closures)
   double *c_Ainv;                 // per instance nc x nc inverse coarse Hessian
   double *c_rhs, *c_sol;          // coarse right-hand side / solution
 };
@@ -119,8 +121,16 @@ struct SolverVecs {
 };
 constexpr int kTraceRec = 8;
 
+// Work descriptor of one CTA of the matrix-free Hessian-vector kernel: poses / landmarks [i0, i1) of instance `inst`
+// (instance-local), plus what the kernel would otherwise fetch through two more dependent loads.
+struct HvBlock {
+  int inst, i0, i1, kind;
+  int z0, pg0, Pi, lg0;  // column base, global index of the instance's first pose, its pose count, first global landmark
+};
+
 struct BlockTables {
-  BlockDesc *rb, *cb, *pb;  // row blocks, column blocks, pose / landmark blocks of the Hessian-vector kernel
+  BlockDesc *rb, *cb;  // row blocks, column blocks
+  HvBlock *pb;         // pose / landmark blocks of the Hessian-vector kernel
   int n_rb, n_cb, n_pb;
   int *rb_begin, *cb_begin, *pb_begin;  // [n_inst+1]
 };
@@ -141,6 +151,7 @@ struct WorkLists {
   int *lists;   // [2][3][n_inst] run / ls / wait per parity, then [n_inst] ev   (flat: no dynamic indexing of
   int *ev;      //  kernel-parameter arrays, which would force a local-memory copy of the parameters)
   int n_inst;
+  int maxvc;                         // most kVecChunk-column chunks any instance has (element-wise vector kernels)
   int maxrb, maxcb, maxseg, maxpb;  // most row blocks / column blocks / chain segments / pose blocks any instance has
   int rb_lo, rb_hi;          // row blocks this rank owns (row-partitioned multi-GPU solve; [0, n_rb) otherwise)
   __device__ __forceinline__ int *list(int parity, int kind) const { return lists + (size_t)(parity * 3 + kind) * n_inst; }

@@ -19,44 +19,62 @@
 
 namespace score {
 
-// incidence codes: kind in the top 3 bits, factor id (global over the batch) below
+// incidence records (16 bytes, one 128-bit load): x = kind (top 3 bits) | factor id (global over the batch); y / z =
+// where the owner's / the partner's translation lives: the z-relative column of its first coordinate with bit 31 set
+// for a pose (coordinate stride d+1; landmark: stride 1); for a relative-pose factor z is the instance-local index of
+// the other pose.  Odometry links (the factor (p-1 -> p) that link_edge names) are NOT in the
+// lists: the kernel takes them straight from link_edge, with the neighbours' blocks at p-1 / p+1.
 enum IncKind : int { INC_EJ = 0, INC_EI = 1, INC_RA = 2, INC_RB = 3, INC_PR = 4 };
 constexpr int kIncShift = 28;
 constexpr int kIncMask = (1 << kIncShift) - 1;
 constexpr int kPosesPerBlock = 256;  // pose block of the Hessian-vector kernel: one thread per pose
 constexpr int kLmPerBlock = 8;       // landmarks per landmark block (handled one after the other by the whole CTA)
+constexpr int kHvTile = 1024;         // range records whose contributions a pose block stages in shared memory at a time
+typedef uint4 IncRec;                 // x: kind | id, y: owner column record, z: partner column record / other pose
 
-// (owner, code) pairs in factor order; owner = global pose index, or P + global landmark index
-__global__ void k_inc_fill(DevProblem P, int *__restrict__ keys, int *__restrict__ vals) {
+__device__ __forceinline__ IncRec inc_make(int kind, int id, unsigned own, unsigned other) {
+  return make_uint4((unsigned)((kind << kIncShift) | id), own, other, 0u);
+}
+
+// (owner, record) pairs in factor order; owner = global pose index, or P + global landmark index; odometry links get
+// the sentinel owner P + L (sorted past every real list)
+__global__ void k_inc_fill(DevProblem P, int *__restrict__ keys, IncRec *__restrict__ vals) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int blk = P.blk, d = P.d;
   if (t < P.E) {
     const int e = (int)t, inst = find_inst(P.edge_off, P.n_inst, e), p0 = P.pose_off[inst];
-    keys[2 * e] = p0 + P.edge_i[e];
-    vals[2 * e] = (INC_EI << kIncShift) | e;
-    keys[2 * e + 1] = p0 + P.edge_j[e];
-    vals[2 * e + 1] = (INC_EJ << kIncShift) | e;
+    const int i = P.edge_i[e], j = P.edge_j[e];
+    const bool link = P.link_edge[p0 + j] == e;
+    keys[2 * e] = link ? P.P + P.L : p0 + i;
+    vals[2 * e] = inc_make(INC_EI, e, 0u, (unsigned)j);
+    keys[2 * e + 1] = link ? P.P + P.L : p0 + j;
+    vals[2 * e + 1] = inc_make(INC_EJ, e, 0u, (unsigned)i);
   } else if (t < (long)P.E + P.K) {
     const int k = (int)(t - P.E), inst = find_inst(P.rng_off, P.n_inst, k);
     const int p0 = P.pose_off[inst], Pi = P.pose_off[inst + 1] - p0, l0 = P.lm_off[inst];
     const int a = P.rng_a[k], b = P.rng_b[k];
+    auto tcol = [&](int o) -> unsigned {
+      return (o < Pi) ? (0x80000000u | (unsigned)(o * blk + d)) : (unsigned)(Pi * blk + (o - Pi) * d);
+    };
     const int j = 2 * P.E + 2 * k;
     keys[j] = (a < Pi) ? p0 + a : P.P + l0 + (a - Pi);
-    vals[j] = (INC_RA << kIncShift) | k;
+    vals[j] = inc_make(INC_RA, k, tcol(a), tcol(b));
     keys[j + 1] = (b < Pi) ? p0 + b : P.P + l0 + (b - Pi);
-    vals[j + 1] = (INC_RB << kIncShift) | k;
+    vals[j + 1] = inc_make(INC_RB, k, tcol(b), tcol(a));
   } else if (t < (long)P.E + P.K + P.Lp) {
     const int q = (int)(t - P.E - P.K), inst = find_inst(P.prior_off, P.n_inst, q);
     const int j = 2 * P.E + 2 * P.K + q;
     keys[j] = P.P + P.lm_off[inst] + P.prior_l[q];
-    vals[j] = (INC_PR << kIncShift) | q;
+    vals[j] = inc_make(INC_PR, q, 0u, 0u);
   }
 }
 
-// inc_ptr from the sorted owners (same construction as k_transpose_fill)
+// inc_ptr from the sorted owners (same construction as k_transpose_fill); owners > n_owner - 1 (the sentinel) end
+// the last real list
 __global__ void k_inc_ptr(int n, int n_owner, const int *__restrict__ sorted_owner, int *__restrict__ ptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int c = sorted_owner[k], cprev = (k == 0) ? -1 : sorted_owner[k - 1];
+  const int c = min(sorted_owner[k], n_owner), cprev = (k == 0) ? -1 : min(sorted_owner[k - 1], n_owner);
   for (int cc = cprev + 1; cc <= c; ++cc) ptr[cc] = k;
   if (k == n - 1)
     for (int cc = c + 1; cc <= n_owner; ++cc) ptr[cc] = n;
@@ -101,7 +119,7 @@ __device__ __forceinline__ void load_trans(const double *x, int z0, int Pi, int 
 
 // u = M_k q for a range (M_k: symmetric d x d, upper row-major, already carrying 2 w)
 template <int D>
-__device__ __forceinline__ void range_apply(const double *__restrict__ mk, const double (&q)[D], double (&u)[D]) {
+__device__ __forceinline__ void range_apply(const double *mk, const double (&q)[D], double (&u)[D]) {
 #pragma unroll
   for (int a = 0; a < D; ++a) {
     double acc = 0.0;
@@ -114,91 +132,184 @@ __device__ __forceinline__ void range_apply(const double *__restrict__ mk, const
   }
 }
 
+// translation at z-relative column record `other` (bit 31: pose, stride d+1)
+template <int D>
+__device__ __forceinline__ void load_trans_rec(const double *xz, unsigned other, double (&t)[D]) {
+  const int col = (int)(other & 0x7fffffffu), stride = (other >> 31) ? D + 1 : 1;
+#pragma unroll
+  for (int r = 0; r < D; ++r) t[r] = xz[col + r * stride];
+}
+
+// Contribution of one relative-pose factor (measurement tm, Rm; doubled precisions k2, tau2) to the h block of one of its
+// poses.  xi: base pose block, xj: `to` pose block.  AT_J: accumulate the `to` pose's part (and the factor's x'Hx
+// term), else the base pose's part.
+template <int D, bool AT_J>
+__device__ __forceinline__ void edge_contrib(const double (&xi)[D * (D + 1)], const double (&xj)[D * (D + 1)],
+                                             const double (&tm)[D], const double (&Rm)[D * D], double k2, double tau2,
+                                             double (&h)[D * (D + 1)], double &quad) {
+  constexpr int D1 = D + 1;
+  double ut[D], uR[D * D], qq = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double qt = xj[r * D1 + D] - xi[r * D1 + D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) qt -= xi[r * D1 + c] * tm[c];
+    ut[r] = k2 * qt;
+    qq += qt * ut[r];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      double qr = xj[r * D1 + c];
+#pragma unroll
+      for (int m = 0; m < D; ++m) qr -= xi[r * D1 + m] * Rm[m * D + c];
+      uR[r * D + c] = tau2 * qr;
+      qq += qr * uR[r * D + c];
+    }
+  }
+  if (AT_J) {
+    quad += qq;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      h[r * D1 + D] += ut[r];
+#pragma unroll
+      for (int c = 0; c < D; ++c) h[r * D1 + c] += uR[r * D + c];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      h[r * D1 + D] -= ut[r];
+#pragma unroll
+      for (int m = 0; m < D; ++m) {
+        double acc = ut[r] * tm[m];
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc += uR[r * D + c] * Rm[m * D + c];
+        h[r * D1 + m] -= acc;
+      }
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void load_edge(const DevProblem &P, int e, double (&tm)[D], double (&Rm)[D * D], double &k2,
+                                          double &tau2) {
+  const double *t = P.edge_t + (size_t)e * D, *R = P.edge_R + (size_t)e * D * D;
+  if (D == 2) {
+    const double2 a = *reinterpret_cast<const double2 *>(t);
+    const double2 b = reinterpret_cast<const double2 *>(R)[0], c = reinterpret_cast<const double2 *>(R)[1];
+    tm[0] = a.x, tm[1] = a.y;
+    Rm[0] = b.x, Rm[1] = b.y, Rm[2] = c.x, Rm[3] = c.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) tm[i] = t[i];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Rm[i] = R[i];
+  }
+  k2 = 2.0 * P.edge_k[e];
+  tau2 = 2.0 * P.edge_tau[e];
+}
+
+// Contribution of a range term to its OWNER's translation block: c = M_k (t_owner - t_partner)  (for the first owner
+// this is +M_k (t_a - t_b), for the second -M_k (t_a - t_b): the same expression).  Returns d.c, the term's x'Hx.
+template <int D>
+__device__ __forceinline__ double range_contrib(const double *xz, const double *mk_all, const IncRec rec, double (&c)[D]) {
+  constexpr int NM = D * (D + 1) / 2;
+  const int id = (int)(rec.x & kIncMask);
+  double to[D], tp[D], m[NM], dv[D];
+  load_trans_rec<D>(xz, rec.y, to);
+  load_trans_rec<D>(xz, rec.z, tp);
+#pragma unroll
+  for (int i = 0; i < NM; ++i) m[i] = mk_all[(size_t)id * NM + i];
+#pragma unroll
+  for (int r = 0; r < D; ++r) dv[r] = to[r] - tp[r];
+  range_apply<D>(m, dv, c);
+  double dc = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) dc += dv[r] * c[r];
+  return dc;
+}
+
 template <int D>
 __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
-  constexpr int D1 = D + 1, BLK = D * D1, NM = D * (D + 1) / 2;
+  constexpr int D1 = D + 1, BLK = D * D1;
   __shared__ double red[16 * (kThreads / 32)];
   __shared__ double qsh;
-  const BlockDesc bd = T.pb[bid];
+  __shared__ double contrib[kHvTile * D];
+  const HvBlock bd = T.pb[bid];
   const int inst = bd.inst;
   if (st[inst].phase != PH_CG || st[inst].eval_now) return;
-  const double *x = V.p;
-  const int z0 = P.zoff[inst], p0 = P.pose_off[inst], Pi = P.pose_off[inst + 1] - p0;
+  const int z0 = bd.z0, Pi = bd.Pi;
+  const double *xz = V.p + z0;  // this instance's block of the direction vector
+  const IncRec *__restrict__ recs = reinterpret_cast<const IncRec *>(P.inc_rec);
+  const int tid = threadIdx.x;
   double quad = 0.0;
   if (bd.kind == CB_POSE) {
-    const int p = bd.i0 + threadIdx.x;  // instance-local pose
-    if (p < bd.i1) {
-      double xo[BLK], h[BLK];
-      load_pose<D>(x, z0, p, xo);
+    const int np = bd.i1 - bd.i0, pgf = bd.pg0 + bd.i0;  // poses of this block, global index of the first one
+    const int p = bd.i0 + tid;                           // instance-local pose of this thread
+    const bool active = tid < np;
+    const int jb = P.inc_ptr[pgf], je = P.inc_ptr[pgf + np];
+    int j0 = 0, j1 = 0;
+    double h[BLK], xo[BLK];
 #pragma unroll
-      for (int i = 0; i < BLK; ++i) h[i] = 0.0;
-      const int j0 = P.inc_ptr[p0 + p], j1 = P.inc_ptr[p0 + p + 1];
-      for (int j = j0; j < j1; ++j) {
-        const int code = P.inc_code[j], kind = code >> kIncShift, id = code & kIncMask;
-        if (kind == INC_EJ || kind == INC_EI) {
-          const bool is_j = kind == INC_EJ;
-          double xn[BLK];  // the other pose of the factor
-          load_pose<D>(x, z0, is_j ? P.edge_i[id] : P.edge_j[id], xn);
-          const double *tm = P.edge_t + (size_t)id * D, *Rm = P.edge_R + (size_t)id * D * D;
-          const double k2 = 2.0 * P.edge_k[id], tau2 = 2.0 * P.edge_tau[id];
-          double xi[BLK], xj[BLK];  // base pose i, `to` pose j
+    for (int i = 0; i < BLK; ++i) h[i] = 0.0;
+    if (active) {
+      // odometry links straight from link_edge: the neighbours' blocks are at p - 1 / p + 1
+      const int e_in = P.link_edge[pgf + tid], e_out = (p + 1 < Pi) ? P.link_edge[pgf + tid + 1] : -1;
+      j0 = P.inc_ptr[pgf + tid];
+      j1 = P.inc_ptr[pgf + tid + 1];
+      load_pose<D>(xz, 0, p, xo);
+      if (e_in >= 0) {  // (p-1 -> p): this pose is the `to` pose
+        double xn[BLK], tm[D], Rm[D * D], k2, tau2;
+        load_pose<D>(xz, 0, p - 1, xn);
+        load_edge<D>(P, e_in, tm, Rm, k2, tau2);
+        edge_contrib<D, true>(xn, xo, tm, Rm, k2, tau2, h, quad);
+      }
+      if (e_out >= 0) {  // (p -> p+1): this pose is the base pose
+        double xn[BLK], tm[D], Rm[D * D], k2, tau2;
+        load_pose<D>(xz, 0, p + 1, xn);
+        load_edge<D>(P, e_out, tm, Rm, k2, tau2);
+        edge_contrib<D, false>(xo, xn, tm, Rm, k2, tau2, h, quad);
+      }
+    }
+    // range terms of the block's poses: their records are one contiguous run [jb, je).  Phase 1: all threads stride
+    // over the run (coalesced 128-bit record loads, independent gathers) and stage each term's contribution in shared
+    // memory; phase 2: every pose adds the contributions of its own list in list order.
+    for (int t0 = jb; t0 < je; t0 += kHvTile) {
+      const int t1 = min(je, t0 + kHvTile);
+#pragma unroll 2
+      for (int j = t0 + tid; j < t1; j += kThreads) {
+        const IncRec rec = recs[j];
+        const int kind = (int)(rec.x >> kIncShift);
+        if (kind == INC_RA || kind == INC_RB) {
+          double c[D];
+          const double dc = range_contrib<D>(xz, V.mk, rec, c);
+          if (kind == INC_RA) quad += dc;  // the term's x'Hx is counted at its first owner
 #pragma unroll
-          for (int i = 0; i < BLK; ++i) {
-            xi[i] = is_j ? xn[i] : xo[i];
-            xj[i] = is_j ? xo[i] : xn[i];
-          }
-          double ut[D], uR[D * D], qq = 0.0;
-#pragma unroll
-          for (int r = 0; r < D; ++r) {
-            double qt = xj[r * D1 + D] - xi[r * D1 + D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) qt -= xi[r * D1 + c] * tm[c];
-            ut[r] = k2 * qt;
-            qq += qt * ut[r];
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              double qr = xj[r * D1 + c];
-#pragma unroll
-              for (int m = 0; m < D; ++m) qr -= xi[r * D1 + m] * Rm[m * D + c];
-              uR[r * D + c] = tau2 * qr;
-              qq += qr * uR[r * D + c];
-            }
-          }
-          if (is_j) {
-            quad += qq;  // the factor's x'Hx term is counted at its `to` pose
-#pragma unroll
-            for (int r = 0; r < D; ++r) {
-              h[r * D1 + D] += ut[r];
-#pragma unroll
-              for (int c = 0; c < D; ++c) h[r * D1 + c] += uR[r * D + c];
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < D; ++r) {
-              h[r * D1 + D] -= ut[r];
-#pragma unroll
-              for (int m = 0; m < D; ++m) {
-                double acc = ut[r] * tm[m];
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc += uR[r * D + c] * Rm[m * D + c];
-                h[r * D1 + m] -= acc;
-              }
-            }
-          }
-        } else if (kind == INC_RA || kind == INC_RB) {
-          const bool is_a = kind == INC_RA;
-          double tn[D], q[D], u[D];
-          load_trans<D>(x, z0, Pi, is_a ? P.rng_b[id] : P.rng_a[id], tn);
-#pragma unroll
-          for (int r = 0; r < D; ++r) q[r] = is_a ? xo[r * D1 + D] - tn[r] : tn[r] - xo[r * D1 + D];
-          range_apply<D>(V.mk + (size_t)id * NM, q, u);
-#pragma unroll
-          for (int r = 0; r < D; ++r) {
-            h[r * D1 + D] += is_a ? u[r] : -u[r];
-            if (is_a) quad += q[r] * u[r];
-          }
+          for (int r = 0; r < D; ++r) contrib[(j - t0) * D + r] = c[r];
         }
       }
+      __syncthreads();
+      if (active) {
+        for (int j = max(j0, t0); j < min(j1, t1); ++j) {
+          if (P.n_nonlink > 0) {  // relative-pose factors that are not odometry links (loop closures): rare, done in place
+            const IncRec rec = recs[j];
+            const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
+            if (kind == INC_EJ || kind == INC_EI) {
+              double xn[BLK], tm[D], Rm[D * D], k2, tau2;
+              load_pose<D>(xz, 0, (int)rec.z, xn);
+              load_edge<D>(P, id, tm, Rm, k2, tau2);
+              if (kind == INC_EJ)
+                edge_contrib<D, true>(xn, xo, tm, Rm, k2, tau2, h, quad);
+              else
+                edge_contrib<D, false>(xo, xn, tm, Rm, k2, tau2, h, quad);
+              continue;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < D; ++r) h[r * D1 + D] += contrib[(j - t0) * D + r];
+        }
+      }
+      __syncthreads();
+    }
+    if (active) {
       double *dst = V.h + z0 + p * BLK;
       if (D == 2) {
         double2 *d2 = reinterpret_cast<double2 *>(dst);
@@ -210,54 +321,47 @@ __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTa
       }
     }
     const double tot = block_sum<kThreads>(quad, red);
-    if (threadIdx.x == 0) V.part_hv[bid] = tot;
+    if (tid == 0) V.part_hv[bid] = tot;
     return;
   }
   // landmark block: landmarks bd.i0 .. bd.i1 (instance-local), each reduced by the whole CTA in fixed order
-  const int l0 = P.lm_off[inst];
   double qtot = 0.0;  // thread 0 only
   for (int q = bd.i0; q < bd.i1; ++q) {
-    const int o = Pi + q;
-    double xo[D];
-    load_trans<D>(x, z0, Pi, o, xo);
     double v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0.0;
-    const int j0 = P.inc_ptr[P.P + l0 + q], j1 = P.inc_ptr[P.P + l0 + q + 1];
-    for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
-      const int code = P.inc_code[j], kind = code >> kIncShift, id = code & kIncMask;
+    const int j0 = P.inc_ptr[P.P + bd.lg0 + q], j1 = P.inc_ptr[P.P + bd.lg0 + q + 1];
+#pragma unroll 2
+    for (int j = j0 + tid; j < j1; j += kThreads) {
+      const IncRec rec = recs[j];
+      const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
       if (kind == INC_PR) {  // w ||l - prior||^2: curvature 2 w
         const double w2 = 2.0 * P.prior_w[id];
 #pragma unroll
         for (int r = 0; r < D; ++r) {
-          v[r] += w2 * xo[r];
-          v[D] += w2 * xo[r] * xo[r];
+          const double xr = xz[Pi * BLK + q * D + r];
+          v[r] += w2 * xr;
+          v[D] += w2 * xr * xr;
         }
         continue;
       }
-      const bool is_a = kind == INC_RA;
-      double tn[D], qv[D], u[D];
-      load_trans<D>(x, z0, Pi, is_a ? P.rng_b[id] : P.rng_a[id], tn);
+      double c[D];
+      const double dc = range_contrib<D>(xz, V.mk, rec, c);
 #pragma unroll
-      for (int r = 0; r < D; ++r) qv[r] = is_a ? xo[r] - tn[r] : tn[r] - xo[r];
-      range_apply<D>(V.mk + (size_t)id * NM, qv, u);
-#pragma unroll
-      for (int r = 0; r < D; ++r) {
-        v[r] += is_a ? u[r] : -u[r];
-        if (is_a) v[D] += qv[r] * u[r];
-      }
+      for (int r = 0; r < D; ++r) v[r] += c[r];
+      if (kind == INC_RA) v[D] += dc;
     }
     const double tot = block_sum16<kThreads>(v, red);  // thread i < 16 holds the total of v[i]
-    if (threadIdx.x < D) V.h[z0 + Pi * BLK + q * D + threadIdx.x] = tot;
-    if (threadIdx.x == D) qsh = tot;
+    if (tid < D) V.h[z0 + Pi * BLK + q * D + tid] = tot;
+    if (tid == D) qsh = tot;
     __syncthreads();
-    if (threadIdx.x == 0) qtot += qsh;
+    if (tid == 0) qtot += qsh;
   }
-  if (threadIdx.x == 0) V.part_hv[bid] = qtot;
+  if (tid == 0) V.part_hv[bid] = qtot;
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_hessvec(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kThreads, 4) k_hessvec(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);

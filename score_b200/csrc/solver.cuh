@@ -53,6 +53,14 @@ __device__ __forceinline__ double barrier_eps(double q, double kap) {
   return e;
 }
 
+// 1 / x from the hardware seed (rcp.approx.ftz.f64, ~23 bits) and one Newton step (~46 bits): a handful of instructions
+// where the IEEE quotient is 20-30.  Used where the quotient feeds an iteration that corrects itself.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(fma(-x, r, 1.0), r, r);
+}
+
 // The same root for G step sizes of one range at once (line search): the G Newton iterations are independent, so
 // running them in lockstep gives the scheduler G divisions to interleave instead of one dependent chain.  `tol` is
 // the relative step at which the iteration stops: phi_mu is the MINIMUM over rho, so its value is second-order
@@ -62,8 +70,11 @@ template <int G>
 __device__ __forceinline__ void barrier_eps_group(const double (&qm)[G], double kap, double tol, double (&e)[G]) {
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const double sq = sqrt(qm[g] * qm[g] + 2.0 * kap);
-    e[g] = fmin((qm[g] >= 0.0) ? kap / (qm[g] + sq) : 0.5 * (sq - qm[g]), 1.0);
+    // starting point from the two asymptotes; single-precision square root and fast reciprocal are plenty for a guess
+    const double sq = (double)sqrtf((float)(qm[g] * qm[g] + 2.0 * kap));
+    double e0 = (qm[g] >= 0.0) ? kap * rcp_fast(qm[g] + sq) : 0.5 * (sq - qm[g]);
+    if (!(e0 > 0.0)) e0 = 0.5 * kap;  // (the rounded square root can cancel qm exactly)
+    e[g] = fmin(e0, 1.0);
   }
   for (int it = 0; it < 6; ++it) {
     bool all = true;
@@ -72,7 +83,9 @@ __device__ __forceinline__ void barrier_eps_group(const double (&qm)[G], double 
       const double eg = e[g];
       const double F = (qm[g] + eg) * eg * (2.0 - eg) - kap * (1.0 - eg);
       const double dF = eg * (2.0 - eg) + (qm[g] + eg) * (2.0 - 2.0 * eg) + kap;
-      double ne = eg - F / dF;
+      // Newton step with the fast reciprocal: the kernel is bound by FP64 instruction issue, the quotient was most of
+      // an iteration, and a step that is exact to 1e-13 relative converges exactly like the exact one
+      double ne = fma(-F, rcp_fast(dF), eg);
       if (!(ne > 0.0)) ne = 0.5 * eg;
       ne = fmin(ne, 1.0);
       all = all && (fabs(ne - eg) <= tol * eg);
@@ -528,9 +541,9 @@ __device__ __forceinline__ void colpass_body(DevProblem P, SolverVecs V, BlockTa
       gg += h * h;
       gz += h * zc;
       zz += zc * zc;
-    } else if (phase == PH_CG) {
-      V.dz[col] += alpha * V.p[col];
-      V.r[col] -= alpha * h;
+    } else if (phase == PH_CG) {  // (explicit fma: k_cg_update performs the same two operations, bit for bit)
+      V.dz[col] = fma(alpha, V.p[col], V.dz[col]);
+      V.r[col] = fma(-alpha, h, V.r[col]);
     } else {
       V.z[col] += step * V.dz[col];
       V.dz[col] = 0.0;
@@ -730,7 +743,7 @@ __device__ __forceinline__ void pupdate_body(SolverVecs V, BlockTables T, const 
   const BlockDesc bd = T.cb[bid];
   if (st[bd.inst].phase != PH_CG) return;
   const double beta = st[bd.inst].beta;
-  for (int col = bd.i0 + threadIdx.x; col < bd.i1; col += kThreads) V.p[col] = V.s[col] + beta * V.p[col];
+  for (int col = bd.i0 + threadIdx.x; col < bd.i1; col += kThreads) V.p[col] = fma(beta, V.p[col], V.s[col]);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
@@ -740,6 +753,83 @@ __global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables 
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxcb; item += gridDim.x) {
     const int inst = act[item / W.maxcb], bid = T.cb_begin[inst] + (int)(item % W.maxcb);
     if (bid < T.cb_begin[inst + 1]) pupdate_body(V, T, st, bid);
+  }
+}
+
+// ---- Element-wise column-space updates of the PCG iteration, 128-bit accesses.  Work item = (listed instance) x
+// (chunk of kVecChunk consecutive columns of that instance): one CTA streams 16 KB per vector.
+constexpr int kVecChunk = 2048;  // doubles per chunk: kThreads threads x 4 double2
+
+// PH_CG (matrix-free operator): dz += alpha p ; r -= alpha h, h = 0 on the pinned pose's columns.
+__global__ void __launch_bounds__(kThreads) k_cg_update(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxvc; item += gridDim.x) {
+    const int inst = act[item / W.maxvc], chunk = (int)(item % W.maxvc);
+    const int z0 = P.zoff[inst], n = P.zoff[inst + 1] - z0, c0 = chunk * kVecChunk;
+    if (c0 >= n || st[inst].phase != PH_CG || st[inst].eval_now) continue;
+    const double alpha = st[inst].alpha;
+    const int c1 = min(n, c0 + kVecChunk), pin = P.blk;
+    double *dz = V.dz + z0, *r = V.r + z0;
+    const double *p = V.p + z0, *h = V.h + z0;
+    if ((z0 & 1) == 0) {
+      const int v0 = c0 / 2, v1 = c1 / 2;  // whole double2 elements
+      for (int v = v0 + threadIdx.x; v < v1; v += kThreads) {
+        const double2 pp = reinterpret_cast<const double2 *>(p)[v];
+        double2 hh = reinterpret_cast<const double2 *>(h)[v];
+        double2 dd = reinterpret_cast<double2 *>(dz)[v], rr = reinterpret_cast<double2 *>(r)[v];
+        if (2 * v < pin) hh.x = 0.0;
+        if (2 * v + 1 < pin) hh.y = 0.0;
+        dd.x = fma(alpha, pp.x, dd.x);
+        dd.y = fma(alpha, pp.y, dd.y);
+        rr.x = fma(-alpha, hh.x, rr.x);
+        rr.y = fma(-alpha, hh.y, rr.y);
+        reinterpret_cast<double2 *>(dz)[v] = dd;
+        reinterpret_cast<double2 *>(r)[v] = rr;
+      }
+      if ((c1 & 1) && c1 == n && threadIdx.x == 0) {  // odd tail column of the instance
+        const int c = c1 - 1;
+        const double hv = c < pin ? 0.0 : h[c];
+        dz[c] = fma(alpha, p[c], dz[c]);
+        r[c] = fma(-alpha, hv, r[c]);
+      }
+    } else {
+      for (int c = c0 + threadIdx.x; c < c1; c += kThreads) {
+        const double hv = c < pin ? 0.0 : h[c];
+        dz[c] = fma(alpha, p[c], dz[c]);
+        r[c] = fma(-alpha, hv, r[c]);
+      }
+    }
+  }
+}
+
+// PH_CG: p = s + beta p  (the vectorised twin of k_pupdate)
+__global__ void __launch_bounds__(kThreads) k_pupdate_vec(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxvc; item += gridDim.x) {
+    const int inst = act[item / W.maxvc], chunk = (int)(item % W.maxvc);
+    const int z0 = P.zoff[inst], n = P.zoff[inst + 1] - z0, c0 = chunk * kVecChunk;
+    if (c0 >= n || st[inst].phase != PH_CG) continue;
+    const double beta = st[inst].beta;
+    const int c1 = min(n, c0 + kVecChunk);
+    double *p = V.p + z0;
+    const double *s = V.s + z0;
+    if ((z0 & 1) == 0) {
+      const int v0 = c0 / 2, v1 = c1 / 2;
+      for (int v = v0 + threadIdx.x; v < v1; v += kThreads) {
+        const double2 ss = reinterpret_cast<const double2 *>(s)[v];
+        double2 pp = reinterpret_cast<double2 *>(p)[v];
+        pp.x = fma(beta, pp.x, ss.x);
+        pp.y = fma(beta, pp.y, ss.y);
+        reinterpret_cast<double2 *>(p)[v] = pp;
+      }
+      if ((c1 & 1) && c1 == n && threadIdx.x == 0) p[c1 - 1] = fma(beta, p[c1 - 1], s[c1 - 1]);
+    } else {
+      for (int c = c0 + threadIdx.x; c < c1; c += kThreads) p[c] = fma(beta, p[c], s[c]);
+    }
   }
 }
 

@@ -154,6 +154,7 @@ class ScoreSolver:
         verbose: int = 0,
         tail_threshold: int = 0,
         operator_mode: int = 0,
+        hi_prio_threshold: int = 0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
@@ -163,6 +164,7 @@ class ScoreSolver:
         prm.verbose = verbose
         prm.tail_threshold = tail_threshold
         prm.operator_mode = operator_mode
+        prm.hi_prio_threshold = hi_prio_threshold
         prm.cg_grow_after, prm.cg_grow_every = cg_grow_after, cg_grow_every
         prm.coarse_every = coarse_every
         prm.stream = C.c_void_p(stream) if stream else None
@@ -283,11 +285,18 @@ class ScoreSolverGroup:
             self.solvers = list(self.pool.map(lambda part: ScoreSolver(part, device=device), self.parts))
 
     def close(self) -> None:
+        for st in getattr(self, "_sets", [self.solvers])[1:]:
+            for s in st:
+                s.close()
+        self._sets = [self.solvers]
         for s in self.solvers:
             if s is not None:
                 s.close()
         self.solvers = [None] * len(self.parts)
         self.pool.shutdown(wait=True)
+        if getattr(self, "_steps_pool", None) is not None:
+            self._steps_pool.shutdown(wait=True)
+            self._steps_pool = None
         if self.pipe_pool is not None:
             self.pipe_pool.shutdown(wait=True)
             self.pipe_pool = None
@@ -317,6 +326,47 @@ class ScoreSolverGroup:
     def solve(self, **kw) -> SolveStats:
         kw.pop("stream", None)  # every handle runs on its own (library-owned, non-blocking) stream
         return self.merge_stats(list(self.pool.map(lambda s: s.solve(**kw), self.solvers)))
+
+    def solve_steps(self, steps: int, n_sets: int = 1, stagger: bool = True, **kw) -> List[SolveStats]:
+        """Solve the whole batch ``steps`` times as a pipeline: every sub-batch handle is re-solved by its own host thread
+        with NO barrier between the steps, the sub-batches starting a fraction of a solve apart.  With ``n_sets`` > 1 the
+        steps are double-buffered over that many sets of handles (step k runs on set k mod n_sets), so that
+        ``n_sets x n_parts`` sub-batch solves are in flight.
+
+        Why: a sweep's last cycles are sparse (a handful of ill-conditioned instances keep a sub-batch alive long after
+        the others have finished) and leave the GPU mostly idle; with several sub-batch solves in flight and out of phase,
+        the tails of some run under the dense first cycles of others (profiles/pipeline_probe_r2.txt).  Returns one merged
+        SolveStats per step.  Per-instance results are bit-identical to ``solve`` (instances never interact)."""
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+
+        kw.pop("stream", None)
+        n = len(self.solvers)
+        n_sets = max(1, min(int(n_sets), steps))
+        if not hasattr(self, "_sets"):
+            self._sets = [self.solvers]
+        while len(self._sets) < n_sets:  # further handle sets over the same sub-batches
+            self._sets.append(list(self.pool.map(lambda part: ScoreSolver(part, device=self.device), self.parts)))
+        if getattr(self, "_steps_pool", None) is None or self._steps_pool._max_workers < n * n_sets:
+            if getattr(self, "_steps_pool", None) is not None:
+                self._steps_pool.shutdown(wait=True)
+            self._steps_pool = ThreadPoolExecutor(n * n_sets)
+        delay = getattr(self, "_last_part_s", 0.0) / (n * n_sets) if stagger else 0.0
+        counts = [len(range(si, steps, n_sets)) for si in range(n_sets)]  # steps served by every set
+
+        def run(job):
+            si, j = divmod(job, n)
+            if delay > 0 and job > 0:
+                time.sleep(job * delay)
+            out = []
+            for _ in range(counts[si]):
+                t0 = time.perf_counter()
+                out.append(self._sets[si][j].solve(**kw))
+                self._last_part_s = time.perf_counter() - t0
+            return out
+
+        per_job = list(self._steps_pool.map(run, range(n * n_sets)))
+        return [self.merge_stats([per_job[(k % n_sets) * n + j][k // n_sets] for j in range(n)]) for k in range(steps)]
 
     def solution(self, out=None):
         shapes = self._shapes()
@@ -349,7 +399,7 @@ class ScoreSolverGroup:
         for h in hs:
             h.close()
 
-    def run_pipelined(self, out=None, steps: int = 1, **kw):
+    def run_pipelined(self, out=None, steps: int = 1, inflight: int = 0, **kw):
         """create -> solve -> read-back -> destroy of every sub-batch in its own thread (the end-to-end path).
 
         ``steps`` > 1 repeats the whole batch that many times as ONE queue of sub-batch jobs (every job uploads its
@@ -365,7 +415,8 @@ class ScoreSolverGroup:
             out = tuple(np.empty(s) for s in self._shapes())
         views = self._views(out)
         n = len(self.parts)
-        solving = threading.Semaphore(self.n_streams)
+        inflight = int(inflight) if inflight > 0 else self.n_streams  # sub-batch solves running at the same time
+        solving = threading.Semaphore(inflight)
         creating = threading.Lock()  # one score_create at a time: concurrent creates only contend (host cores, driver)
         out_locks = [threading.Lock() for _ in range(n)]
 
@@ -384,8 +435,10 @@ class ScoreSolverGroup:
         if steps == 1:
             res = list(self.pool.map(one, range(n)))
         else:
-            if self.pipe_pool is None:  # kept for the life of the group: no thread start-up / tear-down per call
-                self.pipe_pool = ThreadPoolExecutor(self.n_streams + 1)
+            if self.pipe_pool is None or self.pipe_pool._max_workers < inflight + 1:
+                if self.pipe_pool is not None:
+                    self.pipe_pool.shutdown(wait=True)
+                self.pipe_pool = ThreadPoolExecutor(inflight + 1)  # kept for the life of the group
             res = list(self.pipe_pool.map(one, range(steps * n)))
         return (self.merge_stats([r[0] for r in res]), out, sum(r[1] for r in res) // steps,
                 sum(r[2] for r in res) // steps)
