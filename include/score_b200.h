@@ -106,7 +106,7 @@ typedef struct {
   /* interior-point path following (0: defaults) */
   double mu0;              /* initial barrier parameter, default 0.1; < 0: no barrier (plain semismooth Newton) */
   double mu_factor;        /* barrier reduction per centred stage, default 0.1       */
-  double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 16 */
+  double center_tol;       /* stage ends when Newton decrement^2 / mu <= this, default 16 (early stages, mu > 1e-5) */
   double mu_min;           /* smallest barrier parameter, default 1e-16              */
   int32_t cg_grow_after;   /* from this cycle on the PCG ticks per cycle double every cg_grow_every cycles, <=0: never */
   int32_t cg_grow_every;   /* <=0: 8                                                 */
@@ -117,6 +117,9 @@ typedef struct {
                               column pass) */
   int32_t hi_prio_threshold; /* > 0: the cycles after at most this many instances are left unfinished run on a
                               high-priority stream (library-owned stream only); <= 0: never (default; measured: no gain) */
+  int32_t reserved3;
+  double center_tol_late;  /* the same threshold on the last barrier stages (mu <= 1e-5, the ones whose iterates are
+                              certified), default 4 */
 } ScoreParams;
 
 /* Per-instance result record. */

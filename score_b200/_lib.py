@@ -80,6 +80,8 @@ class ScoreParams(C.Structure):
         ("tail_threshold", C.c_int32),
         ("operator_mode", C.c_int32),
         ("hi_prio_threshold", C.c_int32),
+        ("reserved3", C.c_int32),
+        ("center_tol_late", C.c_double),
     ]
 
 

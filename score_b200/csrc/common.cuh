@@ -170,7 +170,7 @@ __device__ __forceinline__ void wl_get(const WorkLists &W, int kind, const int *
 struct SolverCfg {
   int max_newton, max_cg;
   double kkt_tol, forcing;
-  double mu0, mu_factor, mu_min, mu_eval, center_tol, coarse_reg;
+  double mu0, mu_factor, mu_min, mu_eval, center_tol, center_tol_late, coarse_reg;
   int coarse_every, pad;
 };
 

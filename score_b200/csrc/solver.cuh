@@ -389,6 +389,10 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
         step = a;
       }
     }
+    // Below the resolution of the line search: when the predicted decrease (half the Newton decrement^2) is lost in the
+    // rounding of F_mu (~1e-13 relative: a sum of ~1e4 terms), no candidate can be told from a = 0.  The Newton step
+    // itself is still good to many digits there, so take it in full instead of reporting a failed search.
+    if (step == 0.0 && S.ls_shift == 0 && S.dec >= 0.0 && S.dec <= 1e-11 * (1.0 + fabs(best))) step = 1.0;
     S.step = step;
     S.mu_ls = S.mu;
     // path following: once the Newton decrement (in units of mu) says the iterate is centred — or no
@@ -397,9 +401,11 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
     S.want_eval = 0;
     // no decrease although the iterate is not centred: the Newton step is too long for the ladder -> solve the same
     // system again (tighter forcing term, ctrl_b) and search 64x shorter steps; give up on the stage after 3 shifts
-    const bool retry = step == 0.0 && lam2 > cfg.center_tol && S.ls_shift < 3;
+    // (the early stages only have to stay near the path; the last ones feed the certificate and are centred tighter)
+    const double ctol = (S.mu <= cfg.mu_eval) ? cfg.center_tol_late : cfg.center_tol;
+    const bool retry = step == 0.0 && lam2 > ctol && S.ls_shift < 3;
     S.ls_shift = retry ? S.ls_shift + 1 : 0;
-    if (S.mu > 0.0 && !retry && (lam2 <= cfg.center_tol || step == 0.0)) {
+    if (S.mu > 0.0 && !retry && (lam2 <= ctol || step == 0.0)) {
       if (S.mu <= cfg.mu_eval) S.want_eval = 1;
       if (S.mu <= cfg.mu_min) S.stall += 1;
       S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);

@@ -155,6 +155,7 @@ class ScoreSolver:
         tail_threshold: int = 0,
         operator_mode: int = 0,
         hi_prio_threshold: int = 0,
+        center_tol_late: float = 0.0,
     ) -> SolveStats:
         prm = _lib.ScoreParams()
         prm.device = self.device
@@ -165,6 +166,7 @@ class ScoreSolver:
         prm.tail_threshold = tail_threshold
         prm.operator_mode = operator_mode
         prm.hi_prio_threshold = hi_prio_threshold
+        prm.center_tol_late = center_tol_late
         prm.cg_grow_after, prm.cg_grow_every = cg_grow_after, cg_grow_every
         prm.coarse_every = coarse_every
         prm.stream = C.c_void_p(stream) if stream else None
