@@ -193,7 +193,8 @@ int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, const char *id
 
 /* Test / diagnostic access to solver internals of instance `inst` after score_solve (host buffer of
  * `capacity` doubles; *count receives the number of doubles the array has; pass out = NULL to query):
- *   SCORE_INT_COARSE_INV  nc x nc inverse coarse matrix of the last Newton step (0 doubles: coarse level off)
+ *   SCORE_INT_COARSE_INV  nc x nc inverse coarse matrix of the last Newton step (0 doubles: coarse level off; large
+ *                         coarse spaces whose landmark block is eliminated: its nb x nb segment-base block)
  *   SCORE_INT_RANGE_CURV  K_inst x d(d+1)/2 curvature blocks 2 w H_k of the range terms (upper, row-major)
  *   SCORE_INT_FRAMES      P_inst x d x (d+1) dead-reckoned frames of the odometry-chain preconditioner
  *   SCORE_INT_TRACE       (only after a solve with ScoreParams.verbose >= 2) 256 x 8 doubles, one record per Newton

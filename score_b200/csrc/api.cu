@@ -98,6 +98,14 @@ struct ScoreHandle_ {
   // instances with kCoarseMax < nc <= kCoarseBigMax: dense global-memory coarse level (dense.cuh); a handle that is
   // one such instance (c_big) launches its cycles directly and lets the host decide when the level is rebuilt
   std::vector<int> big;
+  // per entry of `big`: landmark block eliminated by its Schur complement (dense.cuh) when no range joins two landmarks
+  struct BigInst {
+    bool schur = false;
+    int ldp = 0;
+    double *S21 = nullptr, *Y = nullptr, *Dinv = nullptr, *part = nullptr, *w = nullptr;
+  };
+  std::vector<BigInst> bigx;
+  std::vector<char> c_ll;  // per instance: some range joins two landmarks
   bool c_big = false;
   double *cb_work = nullptr, *cb_W = nullptr, *cb_raw = nullptr, *cb_scl = nullptr;  // sweep work matrix / panels
   int cb_ldp = 0;
@@ -656,6 +664,7 @@ struct CoarseInstTables {
   std::vector<int> inc_code, drun_slot, drun_begin, pr_code, orun_lo, orun_hi, orun_begin, ws;
   std::vector<double> inc_w2;
   bool bad = false;
+  bool has_ll = false;  // a range between two landmarks (the landmark block of the coarse matrix is then not block diagonal)
 };
 
 static void coarse_tables_one(const ScoreHandle_ *h, int i, const int *rng_a, const int *rng_b, const double *rng_w,
@@ -680,6 +689,7 @@ static void coarse_tables_one(const ScoreHandle_ *h, int i, const int *rng_a, co
       return;
     }
     const int sa = slot_of(a), sb = slot_of(b);
+    if (a >= Pi && b >= Pi) out.has_ll = true;
     sa_v[k] = sa;
     sb_v[k] = sb;
     if (sa >= 0 && sa == sb) {
@@ -764,6 +774,7 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
   }
   SCORE_CUDA_CHECK(fetch_to_host(seg_ptr.data(), desc->seg_ptr, sizeof(int) * (P.n_seg + 1)));
   std::vector<CoarseInstTables> tabs(NI);
+  h->c_ll.assign(NI, 0);
   {
     std::atomic<int> next(0);
     auto worker = [&]() {
@@ -785,6 +796,7 @@ static int build_coarse_tables(ScoreHandle_ *h, const ScoreProblemDesc *desc) {
       g_score_last_error = "range endpoint out of bounds";
       return SCORE_ERR_INVALID;
     }
+    h->c_ll[i] = tabs[i].has_ll ? 1 : 0;
     inc_off[i + 1] = inc_off[i] + (int)tabs[i].inc_code.size();
     drun_off[i + 1] = drun_off[i] + (int)tabs[i].drun_slot.size();
     pr_off[i + 1] = pr_off[i] + (int)tabs[i].pr_code.size();
@@ -1106,6 +1118,21 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     trace.mark("coarse-dims");
     if ((rc = build_coarse_tables(h, desc))) return rc;
     trace.mark("coarse-tables");
+    static const bool no_schur = getenv("SCORE_NO_SCHUR") && atoi(getenv("SCORE_NO_SCHUR")) != 0;  // A/B knob
+    for (int i : h->big) {
+      ScoreHandle_::BigInst b;
+      const int nb = h->c_nb[i], nl = h->c_n[i] - nb;
+      b.schur = !no_schur && nb > 0 && nl > 0 && !h->c_ll[i];
+      if (b.schur) {
+        b.ldp = (nb + 7) & ~7;
+        DA(b.S21, (size_t)nl * b.ldp)
+        DA(b.Y, (size_t)nl * b.ldp)
+        DA(b.Dinv, (size_t)nl * d)
+        DA(b.part, (size_t)kSchurChunks * nb)
+        DA(b.w, nb)
+      }
+      h->bigx.push_back(b);
+    }
   }
   // block tables
   std::vector<BlockDesc> rb, cb;
@@ -1362,16 +1389,52 @@ static void launch_coarse_build(ScoreHandle_ *h, const SolverCfg &cfg, cudaStrea
 // Dense coarse level of a large instance: accumulate into the global-memory work matrix, invert it by blocked
 // symmetric sweeps (dense.cuh; every kernel gated on the instance's phase), symmetrised copy into c_Ainv.
 template <int D>
-static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, int inst, cudaStream_t st) {
+static int launch_coarse_big_build(ScoreHandle_ *h, const SolverCfg &cfg, int bi, cudaStream_t st) {
   const DevProblem &P = h->P;
-  const int n = h->c_n[inst];
+  const int inst = h->big[bi];
+  const ScoreHandle_::BigInst &B = h->bigx[bi];
+  const int n = h->c_n[inst], nb = h->c_nb[inst], nl = n - nb;
   double *A = h->cb_work;
   cudaMemsetAsync(A, 0, sizeof(double) * (size_t)n * n, st);
   k_coarse_big_accum<D><<<h->n_sm * 4, kBigThreads, 0, st>>>(P, h->n_ranks > 1 ? h->Vg : h->V, cfg.coarse_reg, A, inst, h->st);
   k_coarse_big_finish<D><<<grid_for((long)n * n, 256), 256, 0, st>>>(P, A, inst, h->st);
-  const int k = launch_dense_sweep(A, n, n, h->cb_W, h->cb_raw, h->cb_scl, h->cb_ldp, h->st, inst, st);
-  k_dense_finish<<<grid_for((long)n * n, 256), 256, 0, st>>>(A, n, n, P.c_Ainv + h->c_moff[inst], n, h->st, inst);
-  return 3 + k;
+  if (!B.schur) {
+    const int k = launch_dense_sweep(A, n, n, h->cb_W, h->cb_raw, h->cb_scl, h->cb_ldp, h->st, inst, st);
+    k_dense_finish<<<grid_for((long)n * n, 256), 256, 0, st>>>(A, n, n, P.c_Ainv + h->c_moff[inst], n, h->st, inst);
+    return 3 + k;
+  }
+  // landmark block eliminated: T = S11 - S12 Dl^-1 S12^T in place of S11 (the leading nb x nb block of A, stride n)
+  k_schur_prep<D><<<grid_for((long)(nl / D) * nb, 256), 256, 0, st>>>(A, n, nb, B.S21, B.Y, B.Dinv, B.ldp, h->st, inst);
+  const int nt = (nb + kDT - 1) / kDT;
+  k_dense_update<<<dim3(nt, nt), 256, 0, st>>>(A, nb, n, B.S21, B.Y, B.ldp, nl, 0, nullptr, h->st, inst);
+  const int k = launch_dense_sweep(A, nb, n, h->cb_W, h->cb_raw, h->cb_scl, h->cb_ldp, h->st, inst, st);
+  k_dense_finish<<<grid_for((long)nb * nb, 256), 256, 0, st>>>(A, nb, n, P.c_Ainv + h->c_moff[inst], nb, h->st, inst);
+  return 5 + k;
+}
+
+// y = A_c^-1 c of a large instance, then scatter (segment bases -> ytmp, landmarks -> s, partial r.s)
+template <int D>
+static int launch_coarse_big_apply(ScoreHandle_ *h, int bi, cudaStream_t st) {
+  const DevProblem &P = h->P;
+  const int inst = h->big[bi];
+  const ScoreHandle_::BigInst &B = h->bigx[bi];
+  const int n = h->c_n[inst], nb = h->c_nb[inst], nl = n - nb;
+  int k = 0;
+  if (!B.schur) {
+    k_coarse_big_apply<<<grid_for(n, kBigThreads / 32), kBigThreads, 0, st>>>(P, h->st, inst);
+    k = 1;
+  } else {
+    const double *crhs = P.c_rhs + h->c_off[inst];
+    double *sol = P.c_sol + h->c_off[inst];
+    const double *Tinv = P.c_Ainv + h->c_moff[inst];
+    k_schur_apply1<D><<<dim3(grid_for(nb, 256), kSchurChunks), 256, 0, st>>>(B.S21, B.Dinv, crhs, nb, nl, B.ldp, B.part, h->st, inst);
+    k_schur_apply2<<<grid_for(nb, 256), 256, 0, st>>>(crhs, B.part, nb, B.w, h->st, inst);
+    k_schur_matvec<D, false><<<grid_for(nb, 8), 256, 0, st>>>(Tinv, nb, nb, nb, B.w, sol, nullptr, nullptr, h->st, inst);
+    k_schur_matvec<D, true><<<grid_for(nl, 8), 256, 0, st>>>(B.Y, nl, nb, B.ldp, sol, sol + nb, B.Dinv, crhs + nb, h->st, inst);
+    k = 4;
+  }
+  k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st, inst);
+  return k + 1;
 }
 
 static bool coarse_apply_split() {
@@ -1389,20 +1452,18 @@ static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
   // the stand-alone kernel, for A/B measurements; both give the same bits)
   const bool split = coarse_apply_split();
   const bool fuse = h->c_nmax > 0 && !split;
+  int nbig = 0;
   if (h->c_nmax > 0 && split) {
     if (pf) pf->mark(KI_COARSE_APPLY);
     k_coarse_apply<D><<<wgrid(h, P.n_inst, 8), kCoarseApplyThreads, 0, st>>>(P, h->V, h->st, h->W);
   }
   if (!h->big.empty()) {
     if (pf) pf->mark(KI_COARSE_APPLY);
-    for (int inst : h->big) {
-      k_coarse_big_apply<<<grid_for(h->c_n[inst], kBigThreads / 32), kBigThreads, 0, st>>>(P, h->st, inst);
-      k_coarse_big_scatter<D><<<1, kBigThreads, 0, st>>>(P, h->V, h->st, inst);
-    }
+    for (int bi = 0; bi < (int)h->big.size(); ++bi) nbig += launch_coarse_big_apply<D>(h, bi, st);
   }
   if (pf) pf->mark(KI_PRECOND_FWD);
   k_precond_fwd<D><<<wgrid(h, (long)P.n_inst * h->W.maxseg, 16), kSegThreads, 0, st>>>(P, h->V, h->st, h->W, fuse);
-  return 2 + ((h->c_nmax > 0 && split) ? 1 : 0) + 2 * (int)h->big.size();
+  return 2 + ((h->c_nmax > 0 && split) ? 1 : 0) + nbig;
 }
 
 // Row-partitioned solve: sum a buffer over the ranks (out of place; every rank contributes its own rows only).
@@ -1467,7 +1528,7 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   }
   if (build_big) {
     if (pf) pf->mark(KI_COARSE_BUILD);
-    for (int inst : h->big) n += launch_coarse_big_build<D>(h, cfg, inst, st);
+    for (int bi = 0; bi < (int)h->big.size(); ++bi) n += launch_coarse_big_build<D>(h, cfg, bi, st);
   }
   if (pf) pf->mark(KI_COLPASS);
   n += launch_colpass(h, st, TM_LS);
@@ -2169,6 +2230,8 @@ extern "C" int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, do
   switch (which) {
     case SCORE_INT_COARSE_INV:
       n = (int64_t)h->c_n[inst] * h->c_n[inst];
+      for (size_t bi = 0; bi < h->big.size(); ++bi)  // landmark block eliminated: what is stored is T^-1 = (A_c^-1)_ss
+        if (h->big[bi] == inst && h->bigx[bi].schur) n = (int64_t)h->c_nb[inst] * h->c_nb[inst];
       src = P.c_Ainv + h->c_moff[inst];
       break;
     case SCORE_INT_RANGE_CURV:

@@ -139,6 +139,133 @@ __global__ void __launch_bounds__(256) k_dense_finish(const double *__restrict__
   out[(size_t)i * ldo + j] = -0.5 * (A[(size_t)i * lda + j] + A[(size_t)j * lda + i]);
 }
 
+// ---- Schur complement of a block-diagonal landmark block -----------------------------------------------------
+// Coarse matrix A = [[S11, S12], [S12^T, Dl]] with S11 the free segment bases (nb coordinates), Dl the landmarks
+// (nl coordinates).  When no range term joins two landmarks Dl is block diagonal (one d x d block per landmark) and
+//     A^-1 c :  v = Dl^-1 c_l ;  y_s = T^-1 (c_s - S12 v) ;  y_l = v - Dl^-1 S12^T y_s ,      T = S11 - S12 Dl^-1 S12^T ,
+// so only the nb x nb matrix T is swept (BASELINE configs[4]: nb = 1 188 of nc = 4 188: 44x fewer flops than the full
+// sweep) and an application reads T^-1, S21 = S12^T and Y = Dl^-1 S21 (68 MB instead of 140 MB).
+
+// S21[l][i] = A[i][nb + l],  Y = Dl^-1 S21 (both k-major panels, row stride ldp),  Dinv[q] = (d x d block q of Dl)^-1.
+template <int D>
+__global__ void __launch_bounds__(256) k_schur_prep(const double *__restrict__ A, int n, int nb, double *__restrict__ S21,
+                                                   double *__restrict__ Y, double *__restrict__ Dinv, int ldp,
+                                                   const InstState *st, int gate) {
+  if (!dense_gate(st, gate)) return;
+  const int nq = (n - nb) / D;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)nq * nb) return;
+  const int q = (int)(t / nb), i = (int)(t % nb);
+  double Dq[D * D], inv[D * D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      Dq[r * D + c] = A[(size_t)(nb + q * D + r) * n + nb + q * D + c];
+      inv[r * D + c] = (r == c) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < D; ++c) {  // Gauss-Jordan on the SPD block
+    const double piv = 1.0 / Dq[c * D + c];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      Dq[c * D + j] *= piv;
+      inv[c * D + j] *= piv;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      if (r == c) continue;
+      const double f = Dq[r * D + c];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        Dq[r * D + j] -= f * Dq[c * D + j];
+        inv[r * D + j] -= f * inv[c * D + j];
+      }
+    }
+  }
+  double sv[D];
+#pragma unroll
+  for (int m = 0; m < D; ++m) sv[m] = A[(size_t)i * n + nb + q * D + m];
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m) acc += inv[r * D + m] * sv[m];
+    S21[(size_t)(q * D + r) * ldp + i] = sv[r];
+    Y[(size_t)(q * D + r) * ldp + i] = acc;
+  }
+  if (i == 0) {
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) Dinv[(size_t)q * D * D + e] = inv[e];
+  }
+}
+
+constexpr int kSchurChunks = 64;  // landmark-coordinate chunks of the S12 v product (fixed-order two-stage sum)
+
+// v = Dl^-1 c_l for landmark coordinate l
+template <int D>
+__device__ __forceinline__ double schur_v(const double *__restrict__ Dinv, const double *cl, int l) {
+  const int q = l / D, r = l % D;
+  double acc = 0.0;
+#pragma unroll
+  for (int m = 0; m < D; ++m) acc += Dinv[(size_t)q * D * D + r * D + m] * cl[q * D + m];
+  return acc;
+}
+
+// part[ch][i] = sum over the landmark coordinates l of chunk ch of S21[l][i] v[l]
+template <int D>
+__global__ void __launch_bounds__(256) k_schur_apply1(const double *__restrict__ S21, const double *__restrict__ Dinv,
+                                                     const double *crhs, int nb, int nl, int ldp, double *__restrict__ part,
+                                                     const InstState *st, int inst) {
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  __shared__ double vs[512];
+  const int per = (nl + kSchurChunks - 1) / kSchurChunks;
+  const int l0 = blockIdx.y * per, l1 = min(nl, l0 + per);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double acc = 0.0;
+  for (int lb = l0; lb < l1; lb += 512) {
+    const int cnt = min(512, l1 - lb);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += 256) vs[t] = schur_v<D>(Dinv, crhs + nb, lb + t);
+    __syncthreads();
+    if (i < nb)
+      for (int t = 0; t < cnt; ++t) acc += S21[(size_t)(lb + t) * ldp + i] * vs[t];
+  }
+  if (i < nb) part[(size_t)blockIdx.y * nb + i] = acc;
+}
+
+// w = c_s - sum over the chunks (fixed order)
+__global__ void __launch_bounds__(256) k_schur_apply2(const double *crhs, const double *__restrict__ part, int nb,
+                                                     double *__restrict__ w, const InstState *st, int inst) {
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nb) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int ch = 0; ch < kSchurChunks; ++ch) acc += part[(size_t)ch * nb + i];
+  w[i] = crhs[i] - acc;
+}
+
+// out[row] = sum_j M[row][j] x[j]  (one warp per row); SUBV: out[row] = v[row] - that sum with v = Dl^-1 c_l
+template <int D, bool SUBV>
+__global__ void __launch_bounds__(256) k_schur_matvec(const double *__restrict__ M, int rows, int cols, int ldm, const double *x,
+                                                     double *__restrict__ out, const double *__restrict__ Dinv, const double *cl,
+                                                     const InstState *st, int inst) {
+  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double *__restrict__ a = M + (size_t)row * ldm;
+  double acc0 = 0.0, acc1 = 0.0;
+  int j = lane;
+  for (; j + 32 < cols; j += 64) {
+    acc0 += __ldg(a + j) * x[j];
+    acc1 += __ldg(a + j + 32) * x[j + 32];
+  }
+  if (j < cols) acc0 += __ldg(a + j) * x[j];
+  const double tot = warp_sum(acc0 + acc1);
+  if (lane == 0) out[row] = SUBV ? schur_v<D>(Dinv, cl, row) - tot : tot;
+}
+
 // Host side: in-place sweep of A (n x n, row stride lda) -> -A^-1.  W: kDB*kDB doubles, raw/scl: kDB x ldp panels.
 // Returns the number of kernels launched.
 inline int launch_dense_sweep(double *A, int n, int lda, double *W, double *raw, double *scl, int ldp,
