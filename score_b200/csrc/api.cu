@@ -66,6 +66,7 @@ struct ScoreHandle_ {
   int *wl_mem = nullptr;  // backing store of the work lists
   int n_sm = 148;
   int n_clusters = 16;  // co-resident clusters of the fused PCG kernel
+  int *bar_mem = nullptr;  // group barriers of the fused PCG kernel (counter, generation per group)
   InstState *st = nullptr;
   int *d_ndone = nullptr;
   int *h_ndone = nullptr;  // pinned, two slots (double-buffered completion count)
@@ -121,6 +122,7 @@ struct ScoreHandle_ {
   int dist_per = 0;
 };
 
+constexpr int kMaxFusedGroups = 64;
 constexpr int kNumKernels = 13;
 constexpr int kStatSlots = 16;  // ScoreStats per-kernel arrays
 enum KernelId { KI_ROWPASS = 0, KI_LINESEARCH, KI_CTRL_A, KI_ROWUPDATE, KI_COARSE_BUILD, KI_COLPASS, KI_PRECOND_REV,
@@ -1225,6 +1227,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.part_lm, NI)
   DA(h->st, NI)
   DA(h->d_ndone, 1)
+  DA(h->bar_mem, 2 * kMaxFusedGroups)
   DA(h->out_poses, (size_t)P.P * blk)
   DA(h->out_lms, (size_t)P.L * d)
   DA(h->out_round, (size_t)P.P * d * d)
@@ -1630,20 +1633,27 @@ static int launch_tail_cycle(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t
   n += launch_eval_tick<D>(h, cfg, st, pf);
   if (pf) pf->tag = 3;
   if (pf) pf->mark(KI_PCG_FUSED);
-  const int ncl = std::max(1, std::min(h->n_clusters, P.n_inst));
-  cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3(ncl * kClusterSize);
-  lc.blockDim = dim3(kThreads);
-  lc.dynamicSmemBytes = 0;
-  lc.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kClusterSize;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  lc.attrs = at;
-  lc.numAttrs = 1;
-  cudaLaunchKernelEx(&lc, k_pcg_fused<D>, P, h->V, h->T, h->st, cfg, h->d_ndone, h->W, cfg.max_cg + 1);
+  static const bool use_clusters = getenv("SCORE_FUSED_CLUSTERS") && atoi(getenv("SCORE_FUSED_CLUSTERS")) != 0;  // A/B knob
+  if (use_clusters) {
+    const int ncl = std::max(1, std::min(h->n_clusters, P.n_inst));
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ncl * kClusterSize);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kClusterSize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, k_pcg_fused<D, 0>, P, h->V, h->T, h->st, cfg, h->d_ndone, h->W, cfg.max_cg + 1, h->bar_mem);
+  } else {
+    // software-barrier groups: the whole grid must be resident at once (spinning CTAs never yield their SM)
+    const int groups = std::max(1, std::min({h->n_sm * 4 / kGroupSize, P.n_inst, kMaxFusedGroups}));
+    k_pcg_fused<D, 1><<<groups * kGroupSize, kThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, h->W, cfg.max_cg + 1, h->bar_mem);
+  }
   if (pf) pf->mark(KI_CTRL_B);
   k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, h->V, h->T, h->st, cfg, h->d_ndone, TM_FILE, h->W);
   if (pf) pf->mark(-1);
@@ -1805,6 +1815,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     }
     SCORE_CUDA_CHECK(cudaMemcpyAsync(h->st, init.data(), sizeof(InstState) * P.n_inst, cudaMemcpyHostToDevice, st));
     SCORE_CUDA_CHECK(cudaMemsetAsync(h->d_ndone, 0, sizeof(int), st));
+    SCORE_CUDA_CHECK(cudaMemsetAsync(h->bar_mem, 0, sizeof(int) * 2 * kMaxFusedGroups, st));
     {
       // every instance starts in the line-search phase: run[0] = ls[0] = all instances, parity 0
       std::vector<int> wl(16 + 2 * (size_t)P.n_inst, 0);

@@ -23,14 +23,44 @@
 namespace score {
 
 constexpr int kClusterSize = 8;  // CTAs per instance (portable maximum)
+constexpr int kGroupSize = 32;   // CTAs per instance of the software-barrier variant
 
-template <int D>
+// Barrier of the `nb` CTAs that work on one instance: arrival counter + generation in global memory.  Thread 0 of every
+// CTA releases its CTA's writes (__threadfence), arrives, spins on the generation, acquires.  All CTAs of a group must
+// be resident at the same time (the launch keeps the grid below the device's capacity).
+__device__ __forceinline__ void group_barrier(int *cnt, volatile int *gen, int nb) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int g = *gen;
+    if (atomicAdd(cnt, 1) == nb - 1) {
+      *cnt = 0;
+      __threadfence();
+      *gen = g + 1;
+    } else {
+      while (*gen == g) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// BAR = 0: one thread-block cluster per instance, hardware cluster barriers.  BAR = 1: kGroupSize CTAs per instance,
+// software barriers through global memory (more CTAs per instance: every phase is a single round of blocks).
+template <int D, int BAR>
 __global__ void __launch_bounds__(kThreads) k_pcg_fused(DevProblem P, SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg,
-                                                       int *n_done, WorkLists W, int max_iters) {
+                                                       int *n_done, WorkLists W, int max_iters, int *bar_mem) {
   namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
-  const int cid = blockIdx.x / kClusterSize, ncl = gridDim.x / kClusterSize;
+  constexpr int NB = BAR ? kGroupSize : kClusterSize;
+  const int crank = BAR ? (int)(blockIdx.x % NB) : (int)cg::this_cluster().block_rank();
+  const int cid = blockIdx.x / NB, ncl = gridDim.x / NB;
+  auto sync_all = [&]() {
+    if (BAR)
+      group_barrier(bar_mem + 2 * cid, bar_mem + 2 * cid + 1, NB);
+    else
+      cg::this_cluster().sync();
+  };
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
@@ -48,42 +78,42 @@ __global__ void __launch_bounds__(kThreads) k_pcg_fused(DevProblem P, SolverVecs
       // phase written by CTA 0 before the last barrier of the previous iteration: the same value in every CTA
       if (st[inst].phase != PH_CG || st[inst].eval_now) break;
       // ---- q = B p, u = H_r q, partial p'Hp
-      for (int bid = rb0 + crank; bid < rb1; bid += kClusterSize) {
+      for (int bid = rb0 + crank; bid < rb1; bid += NB) {
         rowpass_body<D, false>(P, V, T, st, bid);
         __syncthreads();
       }
-      cluster.sync();
+      sync_all();
       // ---- step length
       if (crank == 0 && warp0) ctrl_a_body(V, T, st, cfg, inst);
-      cluster.sync();
+      sync_all();
       // ---- h = B^T u, dz += alpha p, r -= alpha h
-      for (int bid = cb0 + crank; bid < cb1; bid += kClusterSize) {
+      for (int bid = cb0 + crank; bid < cb1; bid += NB) {
         colpass_body<false>(P, V, T, st, TM_CG, CS_FUSED, bid);
         __syncthreads();
       }
-      cluster.sync();
+      sync_all();
       // ---- s = P r: reverse scans (+ coarse right-hand side), then coarse solve + forward scans
       if (threadIdx.x < kSegThreads)
-        for (int j = crank; j <= nseg; j += kClusterSize) {
+        for (int j = crank; j <= nseg; j += NB) {
           precond_rev_body<D, true>(P, V, st, j < nseg ? sg0 + j : P.n_seg + inst);
           seg_bar<true>();
         }
-      cluster.sync();
+      sync_all();
       if (threadIdx.x < kSegThreads)
-        for (int j = crank; j < nseg; j += kClusterSize) {
+        for (int j = crank; j < nseg; j += NB) {
           precond_fwd_body<D, true>(P, V, st, sg0 + j, true);
           seg_bar<true>();
         }
-      cluster.sync();
+      sync_all();
       // ---- r.s, beta, convergence
       if (crank == 0 && warp0) {
         ctrl_b_body(P, V, T, st, cfg, n_done, TM_CG, inst);
         if (threadIdx.x == 0) st[inst].fused_cg += 1;
       }
-      cluster.sync();
+      sync_all();
       // ---- p = s + beta p
-      for (int bid = cb0 + crank; bid < cb1; bid += kClusterSize) pupdate_body(V, T, st, bid);
-      cluster.sync();
+      for (int bid = cb0 + crank; bid < cb1; bid += NB) pupdate_body(V, T, st, bid);
+      sync_all();
     }
   }
 }

@@ -14,8 +14,8 @@ for name in ["man1", "goats", "man4", "mc0"]:
     with ScoreSolver(lower_factor_graph(fg)) as s:
         out = {}
         for mode, thr in (("lockstep", 0), ("fused", 1)):
-            s.solve(tail_threshold=thr)
-            st = s.solve(tail_threshold=thr)
+            s.solve(tail_threshold=thr, operator_mode=1)
+            st = s.solve(tail_threshold=thr, operator_mode=1)
             out[mode] = (st, [a.copy() for a in s.solution()])
             r = st.instances[0]
             print(f"{name} {mode}: solved={r['solved']} newton={r['newton_iters']} cg={r['cg_iters']} kkt={r['rel_kkt']:.2e} "
@@ -26,8 +26,8 @@ probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BAS
                                 with_names=False) for i in (838, 201, 173, 276, 462, 963, 181, 889, 551)]
 with ScoreSolver(concat(probs)) as s:
     for mode, thr in (("lockstep", 0), ("fused", 64), ("fused<=4", 4)):
-        s.solve(tail_threshold=thr)
-        st = s.solve(tail_threshold=thr)
+        s.solve(tail_threshold=thr, operator_mode=1)
+        st = s.solve(tail_threshold=thr, operator_mode=1)
         sol = [a.copy() for a in s.solution()]
         if mode == "lockstep":
             ref = sol
