@@ -92,7 +92,7 @@ struct ScoreHandle_ {
   // row-partitioned multi-GPU solve of one instance (score_comm_init)
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
-  double *red_send = nullptr, *red_recv = nullptr;  // [part_row n_rb | part_upd 2 n_rb | h nz]
+  double *red_send = nullptr, *red_recv = nullptr;  // [part_row n_rb | part_upd 4 n_rb | h nz]
   double *ls_recv = nullptr, *mk_recv = nullptr;
   size_t red_count = 0;
   SolverVecs Vg{};  // V with the reduced (global) partial sums / curvature blocks / h
@@ -1207,11 +1207,11 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     SCORE_CUDA_CHECK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
     h->n_clusters = std::max(1, h->n_sm / kClusterSize - 2);  // (GPC boundaries leave a few SMs outside any cluster)
   }
-  h->red_count = 3 * rb.size() + (size_t)P.nz;
+  h->red_count = 5 * rb.size() + (size_t)P.nz;
   DA(h->red_send, h->red_count)
   V.part_row = h->red_send;
   V.part_upd = h->red_send + rb.size();
-  V.hloc = h->red_send + 3 * rb.size();
+  V.hloc = h->red_send + 5 * rb.size();
   V.hglob = V.hloc;
   DA(V.part_ls, rb.size() * kLsSums)
   h->W.rb_lo = 0;
@@ -1952,7 +1952,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   // ---- 4. extraction
   k_split_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z, h->out_poses, h->out_lms);
   k_round_so<<<grid_for(P.P, 128), 128, 0, st>>>(d, P.P, h->out_poses, P.blk, d + 1, h->out_round);
-  if (P.K > 0) k_distances<<<grid_for(P.K, 256), 256, 0, st>>>(P, V.z, h->out_dist);
+  if (P.K > 0) k_distances<<<grid_for(P.K, 256), 256, 0, st>>>(P, V.z, h->st, h->out_dist);
   launches += 3;
   SCORE_CUDA_CHECK(cudaEventRecord(ev[4], st));
   SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -2212,7 +2212,7 @@ extern "C" int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, con
   h->Vg = h->V;
   h->Vg.part_row = h->red_recv;
   h->Vg.part_upd = h->red_recv + n_rb;
-  h->Vg.hglob = h->red_recv + 3 * (size_t)n_rb;
+  h->Vg.hglob = h->red_recv + 5 * (size_t)n_rb;
   h->Vg.part_ls = h->ls_recv;
   h->Vg.mk = h->mk_recv;
   SCORE_CUDA_CHECK(cudaDeviceSynchronize());

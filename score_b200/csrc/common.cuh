@@ -44,6 +44,7 @@ struct InstState {
   int fused_cg, pad0;                      // PCG iterations done inside the fused kernel (fused.cuh)
   double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
+  double mu_out;                           // barrier parameter of the auxiliary variables the last certificate was taken with
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
 };
 
@@ -105,7 +106,7 @@ struct SolverVecs {
   // partial sums
   double *part_row;  // [n_row_blocks] pHp
   double *part_ls;   // [n_row_blocks * kLsSums]
-  double *part_upd;  // [n_row_blocks * 2]  F, |delta|^2
+  double *part_upd;  // [n_row_blocks * 4]  F ; evaluation ticks also |delta|^2, sum lambda s, sum min(lambda, s)^2
   double *hloc;      // [nz] B^T u of this rank's rows (row-partitioned solve: SpMV and update are separate passes)
   const double *hglob;  // [nz] its sum over the ranks
   double *part_col;  // [n_col_blocks * 4]  |g|^2, g.z, |z|^2

@@ -8,6 +8,7 @@
 //          cyclic Jacobi sweeps; no singular-value division, so rank-deficient M is handled too.
 #pragma once
 #include "common.cuh"
+#include "solver.cuh"
 
 namespace score {
 
@@ -103,9 +104,12 @@ __global__ void k_round_so(int d, long n, const double *__restrict__ mats, long 
   for (int i = 0; i < d * d; ++i) out[p * d * d + i] = R[i];
 }
 
-// Exact minimisers of the auxiliary variables given (t, l)  (SURVEY.md App. A.4):
-//   QCQP: delta_k = proj_ball((t_a - t_b) / r~)      SOCP: delta_k = max(r~, ||t_a - t_b||)
-__global__ void k_distances(DevProblem P, const double *__restrict__ z, double *dist) {
+// Auxiliary variables given (t, l): the point of the central path the solve was certified at (barrier parameter
+// InstState::mu_out; the reference's barrier solver returns such interior values too), or, for mu_out = 0, their exact
+// minimisers:
+//   QCQP: delta_k = rho v / n, rho = 1 - eps(n / r~, mu / (w r~^2))      (mu = 0: proj_ball(v / r~)),  v = t_a - t_b
+//   SOCP: delta_k = n + r~ (1 - rho)                                      (mu = 0: max(r~, n))  — the same cost, cone-feasible
+__global__ void k_distances(DevProblem P, const double *__restrict__ z, const InstState *st, double *dist) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.K) return;
   const int d = P.d;
@@ -119,11 +123,13 @@ __global__ void k_distances(DevProblem P, const double *__restrict__ z, double *
     v[r] = z[ca] - z[cb];
     n2 += v[r] * v[r];
   }
-  const double nv = sqrt(n2), rr = P.rng_dist[k];
+  const double nv = sqrt(n2), rr = P.rng_dist[k], mu = st[inst].mu_out;
+  double rho = 0.0;  // dist == 0: the delta column is all zeros, any value does
+  if (rr > 0.0) rho = (mu > 0.0) ? 1.0 - barrier_eps(nv / rr, mu / (P.rng_w[k] * rr * rr)) : fmin(1.0, nv / rr);
   if (P.relax == SCORE_RELAX_SOCP) {
-    dist[k] = fmax(rr, nv);
+    dist[k] = (rr > 0.0) ? nv + rr * (1.0 - rho) : nv;
   } else {
-    const double sc = (rr > 0.0) ? ((nv > rr) ? 1.0 / nv : 1.0 / rr) : 0.0;
+    const double sc = (nv > 0.0) ? rho / nv : 0.0;
     for (int r = 0; r < d; ++r) dist[(size_t)k * d + r] = v[r] * sc;
   }
 }

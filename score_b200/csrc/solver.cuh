@@ -98,6 +98,7 @@ __device__ __forceinline__ void barrier_eps_group(const double (&qm)[G], double 
 // One range term at distance n: value phi_mu(n), tan = phi'/(2 w n), rad = phi''/(2 w).
 struct RangeTerm {
   double val, tan, rad;
+  double rho, gapr;  // norm of the auxiliary variable delta = rho v / n and the residual n - r rho it leaves
 };
 __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, double mu, bool need_val) {
   RangeTerm t;
@@ -105,6 +106,8 @@ __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, do
     t.val = w * n * n;
     t.tan = 1.0;
     t.rad = 1.0;
+    t.rho = 0.0;
+    t.gapr = n;
     return t;
   }
   if (mu == 0.0) {  // exact elimination: w max(0, n - r)^2
@@ -113,6 +116,8 @@ __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, do
     t.val = act ? w * e * e : 0.0;
     t.tan = act ? e / n : 0.0;
     t.rad = act ? 1.0 : 0.0;
+    t.rho = act ? 1.0 : n / r;
+    t.gapr = act ? e : 0.0;
     return t;
   }
   const double q = n / r, kap = mu / (w * r * r);
@@ -121,11 +126,10 @@ __device__ __forceinline__ RangeTerm range_term(double n, double r, double w, do
   const double c = kap * (1.0 + rho * rho) / (om * om);
   t.rad = c / (1.0 + c);
   t.tan = (q > 0.0) ? (q - 1.0 + e) / q : t.rad;
+  t.rho = rho;
+  t.gapr = r * (q - 1.0 + e);
   t.val = 0.0;
-  if (need_val) {
-    const double gap = r * (q - 1.0 + e);
-    t.val = w * gap * gap - mu * log(om);
-  }
+  if (need_val) t.val = w * t.gapr * t.gapr - mu * log(om);
   return t;
 }
 
@@ -405,7 +409,9 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
     const double ctol = (S.mu <= cfg.mu_eval) ? cfg.center_tol_late : cfg.center_tol;
     const bool retry = step == 0.0 && lam2 > ctol && S.ls_shift < 3;
     S.ls_shift = retry ? S.ls_shift + 1 : 0;
-    if (S.mu > 0.0 && !retry && (lam2 <= ctol || step == 0.0)) {
+    // a decrement at the resolution of F_mu itself cannot be driven lower: the stage is as centred as it gets
+    const bool at_floor = S.mu <= cfg.mu_eval && S.dec <= 1e-11 * (1.0 + fabs(best));
+    if (S.mu > 0.0 && !retry && (lam2 <= ctol || at_floor || step == 0.0)) {
       if (S.mu <= cfg.mu_eval) S.want_eval = 1;
       if (S.mu <= cfg.mu_min) S.stall += 1;
       S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
@@ -443,10 +449,15 @@ __device__ __forceinline__ void rowupdate_body(DevProblem P, SolverVecs V, Block
   if (st[inst].phase == PH_DONE) return;
   if (eval ? !st[inst].eval_now : (st[inst].phase != PH_LS || st[inst].eval_now)) return;
   const double step = eval ? 0.0 : st[inst].step;
-  const double mu = eval ? 0.0 : st[inst].mu;
+  // Evaluation ticks certify the point x = (z, delta) with delta on the central path of the barrier parameter the
+  // iterate was last centred for (mu_ls): any delta in the unit ball is feasible, and with this one the stationarity
+  // residual in z is the gradient the Newton iteration drives to zero, while the complementarity terms are bounded by
+  // mu.  (With the exact minimiser delta = proj(v / r), mu = 0, weakly active ranges keep the residual of order
+  // sqrt(w mu) until mu is tiny: a handful of instances then needed mu = 1e-14 and thousands of PCG iterations.)
+  const double mu = eval ? st[inst].mu_ls : st[inst].mu;
   const int rr0 = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * P.rpe;
   const int rr1 = rr0 + (P.rng_off[inst + 1] - P.rng_off[inst]) * D;
-  double Facc = 0.0, dacc = 0.0;
+  double Facc = 0.0, dacc = 0.0, gacc = 0.0, sacc = 0.0;  // objective, |delta|^2, sum lambda s, sum min(lambda, s)^2
   auto plain = [&](int r0, int r1) {
     for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
       const double wr = P.w[row];
@@ -472,8 +483,8 @@ __device__ __forceinline__ void rowupdate_body(DevProblem P, SolverVecs V, Block
         n2 += v[c] * v[c];
       }
       const double nv = sqrt(n2);
-      const RangeTerm t = range_term(nv, rr, wr, mu, true);
-      Facc += t.val;
+      const RangeTerm t = range_term(nv, rr, wr, mu, !eval);
+      Facc += eval ? wr * t.gapr * t.gapr : t.val;  // (certificate: the objective itself, without the barrier term)
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         if (!eval) V.res[row + c] = v[c];
@@ -488,16 +499,26 @@ __device__ __forceinline__ void rowupdate_body(DevProblem P, SolverVecs V, Block
 #pragma unroll
           for (int b = a; b < D; ++b) mk[m++] = 2.0 * wr * (((a == b) ? t.tan : 0.0) + coef * v[a] * v[b]);
       } else if (rr > 0.0) {
-        const double dn = fmin(1.0, nv / rr);
-        dacc += dn * dn;
+        const double lam = 2.0 * wr * rr * t.gapr, sl = 1.0 - t.rho;  // multiplier ||g_delta|| and slack of the ball
+        dacc += t.rho * t.rho;
+        gacc += lam * sl;
+        sacc += fmin(lam, sl) * fmin(lam, sl);
       }
     }
   }
   const double Ftot = block_sum<kThreads>(Facc, red);
+  if (!eval) {
+    if (threadIdx.x == 0) V.part_upd[(size_t)bid * 4 + 0] = Ftot;
+    return;
+  }
   const double dtot = block_sum<kThreads>(dacc, red);
+  const double gtot = block_sum<kThreads>(gacc, red);
+  const double stot = block_sum<kThreads>(sacc, red);
   if (threadIdx.x == 0) {
-    V.part_upd[(size_t)bid * 2 + 0] = Ftot;
-    V.part_upd[(size_t)bid * 2 + 1] = dtot;
+    V.part_upd[(size_t)bid * 4 + 0] = Ftot;
+    V.part_upd[(size_t)bid * 4 + 1] = dtot;
+    V.part_upd[(size_t)bid * 4 + 2] = gtot;
+    V.part_upd[(size_t)bid * 4 + 3] = stot;
   }
 }
 
@@ -620,17 +641,23 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
     // certificate of the un-smoothed problem with the auxiliary variables at their
     // exact minimisers: r_link = 0, r_stat = |g_free| / (1 + |x|), p - D = g_free . z
     const int cb0 = T.cb_begin[inst], cb1 = T.cb_begin[inst + 1];
-    const double F = ctrl_sum(V.part_upd, rb0, rb1, 2, 0);
-    const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 2, 1);
+    const double F = ctrl_sum(V.part_upd, rb0, rb1, 4, 0);
+    const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 4, 1);
+    const double gsum = ctrl_sum(V.part_upd, rb0, rb1, 4, 2);
+    const double ssum = ctrl_sum(V.part_upd, rb0, rb1, 4, 3);
     const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0);
     const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1);
     const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2);
     if (lane != 0) return;
+    // SURVEY.md App. A.7 at x = (z, delta): r_stat = ||x - proj_C(x - g)|| / (1 + ||x||) with min(lambda, s) per range in
+    // the delta block; p - D = g_free . z + sum lambda s
+    const double pd = gz + gsum;
     S.F = F;
-    S.gnorm = sqrt(gg);
+    S.gnorm = sqrt(gg + ssum);
     S.xnorm = sqrt(zz + dn2);
     S.r_stat = S.gnorm / (1.0 + S.xnorm);
-    S.r_gap = fabs(gz) / (1.0 + fabs(F) + fabs(F - gz));
+    S.r_gap = fabs(pd) / (1.0 + fabs(F) + fabs(F - pd));
+    S.mu_out = S.mu_ls;
     S.kkt = fmax(S.r_stat, S.r_gap);
     S.n_eval += 1;
     S.eval_now = 0;
@@ -668,7 +695,7 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
   if (mode != TM_LS || phase != PH_LS) return;
   double rs_new = ctrl_sum(V.part_seg, P.seg_begin[inst], P.seg_begin[inst + 1], 1, 0);
   // PH_LS: a new point (or the initial point) has just been evaluated with barrier parameter S.mu
-  const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 2, 0);
+  const double Fmu = ctrl_sum(V.part_upd, rb0, rb1, 4, 0);
   if (lane != 0) return;
   rs_new += V.part_lm[inst];
   S.Fmu = Fmu;
