@@ -119,7 +119,7 @@ typedef struct {
                               high-priority stream (library-owned stream only); <= 0: never (default; measured: no gain) */
   int32_t reserved3;
   double center_tol_late;  /* the same threshold on the last barrier stages (mu <= 1e-5, the ones whose iterates are
-                              certified), default 4 */
+                              certified), default 1 */
 } ScoreParams;
 
 /* Per-instance result record. */

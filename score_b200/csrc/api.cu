@@ -1692,7 +1692,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   cfg.mu0 = prm.mu0 > 0 ? prm.mu0 : (prm.mu0 < 0 ? 0.0 : 0.1);
   cfg.mu_factor = (prm.mu_factor > 0 && prm.mu_factor < 1) ? prm.mu_factor : 0.1;
   cfg.center_tol = prm.center_tol > 0 ? prm.center_tol : 16.0;
-  cfg.center_tol_late = prm.center_tol_late > 0 ? prm.center_tol_late : 4.0;
+  cfg.center_tol_late = prm.center_tol_late > 0 ? prm.center_tol_late : 1.0;
   cfg.mu_min = prm.mu_min > 0 ? prm.mu_min : 1e-16;
   cfg.mu_eval = 1e-5;
   cfg.coarse_reg = 1e-6;
