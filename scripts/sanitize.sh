@@ -19,7 +19,16 @@ probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BAS
 with ScoreSolver(concat(probs)) as s:
     st = s.solve()
     s.solution()
-    print("batch solved", st.n_solved, "of 7")
+    print("batch solved", st.n_solved, "of 7 (matrix-free operator)")
+    st = s.solve(operator_mode=1)
+    print("batch solved", st.n_solved, "of 7 (assembled CSR pair)")
+    st = s.solve(operator_mode=1, tail_threshold=4)
+    print("batch solved", st.n_solved, "of 7 (fused per-instance PCG kernel for the last 4)")
+from score_b200.lowering import lower_grid3d_arrays
+big = lower_grid3d_arrays(generators.grid_3d_arrays(5, n_robots=12, n_steps=12, grid=8, n_landmarks=20, n_ranges=1500))
+with ScoreSolver(big) as s:
+    st = s.solve()
+    print("3D graph with a large coarse space (Schur complement + blocked sweeps) solved", st.n_solved, "newton", st.instances[0]["newton_iters"])
 PY
 for tool in memcheck racecheck; do
   timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1

@@ -527,3 +527,77 @@ def test_edge_case_graphs_match_oracle(built_lib, kind, relax):
         assert so.kkt_qcqp(prob, x)["rel_kkt"] <= 1e-6
     nz = pq.P * 6
     assert np.abs(poses.ravel() - xq[:nz]).max() <= 1e-3  # single pinned chain: unique optimum
+
+
+@pytest.mark.parametrize("name", ["goats", "man4", "grid3d", "loops"])
+def test_matrix_free_operator_matches_assembled_pair(built_lib, golden, name):
+    """PCG iterations with the factor-wise Hessian-vector product (k_hessvec, the default) against the same solve on the
+    assembled CSR pair (row pass + column pass): same optimum to rounding, both certified by the oracle's evaluator.
+    `loops` has relative-pose factors that are not odometry links (loop closures across a broken chain)."""
+    from oracle import score_oracle as so
+    from score_b200 import generators
+
+    if name == "grid3d":
+        fg = generators.grid_3d_factor_graph(
+            generators.grid_3d_arrays(11, n_robots=3, n_steps=40, grid=8, n_landmarks=5, n_ranges=260))
+    elif name == "loops":
+        fg = _edge_case_graph("broken_chain")
+    else:
+        fg, _ = golden(name)
+    prob = so.assemble(fg, so.QCQP)
+    out = {}
+    with _solver(fg) as s:
+        for mode in (0, 1):
+            st = s.solve(operator_mode=mode, kkt_tol=1e-8)
+            out[mode] = (st.instances[0].copy(), [a.copy() for a in s.solution()])
+    for mode in (0, 1):
+        rec, (poses, rounded, lms, dist) = out[mode]
+        assert rec["solved"] == 1
+        assert so.kkt_qcqp(prob, _full_x(prob, poses, lms, dist))["rel_kkt"] <= 1e-8
+    f0, f1 = out[0][0]["objective"], out[1][0]["objective"]
+    assert abs(f0 - f1) <= 1e-7 * max(1.0, abs(f1))
+    d = prob.dim
+    if name in ("goats", "loops"):  # single pinned chain: unique optimum
+        assert np.abs(out[0][1][0][:, :, d] - out[1][1][0][:, :, d]).max() <= 1e-4
+
+
+def test_fused_pcg_kernel_is_bit_identical_to_lockstep_ticks(built_lib, golden):
+    """The opt-in fused per-instance PCG kernel (fused.cuh) calls the same block-level bodies with the same block
+    decomposition as the lockstep tick kernels: identical bits (both on the assembled CSR pair)."""
+    from score_b200.lowering import concat, lower_factor_graph
+    from score_b200.solver import ScoreSolver
+
+    batch = concat([lower_factor_graph(golden(n)[0]) for n in ("man1", "mc0_small", "goats")])
+    with ScoreSolver(batch) as s:
+        st0 = s.solve(operator_mode=1)
+        ref = [a.copy() for a in s.solution()]
+        st1 = s.solve(operator_mode=1, tail_threshold=8)
+        got = s.solution()
+    assert st0.n_solved == 3 and st1.n_solved == 3
+    assert np.array_equal(st0.instances["cg_iters"], st1.instances["cg_iters"])
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+
+
+def test_pipelined_steps_match_plain_solve_bitwise(built_lib):
+    """ScoreSolverGroup.solve_steps (steps double-buffered over two sets of handles, no barrier between steps): every
+    step's per-instance records and the final solution equal a plain single-handle solve bit for bit."""
+    from score_b200 import generators
+    from score_b200.lowering import concat, lower_manhattan_arrays
+    from score_b200.solver import ScoreSolver, ScoreSolverGroup
+
+    batch = concat([lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=4, n_steps=30))
+                    for i in range(6)])
+    with ScoreSolver(batch) as s:
+        st = s.solve()
+        ref = s.solution()
+    with ScoreSolverGroup(batch, n_streams=2) as g:
+        steps = g.solve_steps(5, n_sets=2)
+        got = g.solution()
+    assert len(steps) == 5
+    for k in steps:
+        assert k.n_solved == 6
+        assert np.array_equal(k.instances["cg_iters"], st.instances["cg_iters"])
+        assert np.array_equal(k.instances["objective"], st.instances["objective"])
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)

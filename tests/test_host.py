@@ -443,3 +443,91 @@ def test_streamed_pipeline_queue_semantics(monkeypatch):
     assert (h2d, d2h) == (100 * 4, 10 * 4)  # per step
     assert np.all(out[0] == 2.0)  # every pose row was written by a 2-instance part
     assert sorted(state["readbacks"]) == sorted([g.parts[0].P, g.parts[1].P] * 3)
+
+
+def test_pipelined_steps_schedule(monkeypatch):
+    """ScoreSolverGroup.solve_steps without a device: K steps double-buffered over n_sets handle sets — every (set, part)
+    handle is re-solved by its own thread, sets x parts solves in flight at most, one merged record per step, and a
+    handle is never solved by two threads at once."""
+    import threading
+    import time
+
+    from score_b200 import generators, solver as solver_mod
+    from score_b200.lowering import concat, lower_manhattan_arrays
+
+    probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=2, n_steps=6))
+             for i in range(4)]
+    batch = concat(probs)
+    lock = threading.Lock()
+    state = {"solving": 0, "max_solving": 0, "handles": 0, "overlap": False}
+
+    class FakeSolver:
+        def __init__(self, prob, device=0):
+            self.prob, self.busy, self.count = prob, False, 0
+            with lock:
+                state["handles"] += 1
+
+        def close(self):
+            pass
+
+        def solve(self, **kw):
+            with lock:
+                state["overlap"] |= self.busy
+                self.busy = True
+                state["solving"] += 1
+                state["max_solving"] = max(state["max_solving"], state["solving"])
+            time.sleep(0.02)
+            with lock:
+                self.busy = False
+                state["solving"] -= 1
+                self.count += 1
+            n = self.prob.n_instances
+            inst = np.zeros(n, dtype=solver_mod._INST_DTYPE)
+            inst["solved"] = 1
+            z = np.zeros(len(solver_mod.KERNEL_NAMES))
+            return solver_mod.SolveStats(n, n, 5, 7, 0.0, 0.0, 1.0, 0.0, 1.0, 0, 0, 0, 0.0, inst, kernel_ms=z,
+                                         kernel_bytes=z, kernel_count=z, kernel_bytes_total=z, cycles=1)
+
+    monkeypatch.setattr(solver_mod, "ScoreSolver", FakeSolver)
+    g = solver_mod.ScoreSolverGroup(batch, n_streams=2)
+    steps = g.solve_steps(5, n_sets=2)
+    assert len(steps) == 5 and all(s.n_instances == 4 and s.n_solved == 4 for s in steps)
+    assert state["handles"] == 4 and not state["overlap"]  # 2 sets x 2 parts, each handle used by one thread at a time
+    assert 2 <= state["max_solving"] <= 4
+    counts = sorted(s.count for st in g._sets for s in st)
+    assert counts == [2, 2, 3, 3]  # set 0 serves steps 0, 2, 4; set 1 serves steps 1, 3
+    g.close()
+
+
+def test_g2o_roundtrip(tmp_path):
+    """g2o text (README.md:53-56 names it as the interchange format PyFactorGraph reads) -> FactorGraphData: what the
+    SCORE cost reads survives a write / parse round trip bit for bit (2D multi-robot graph with ranges, 3D graph)."""
+    from py_factor_graph.parsing.parse_g2o_file import parse_g2o_file, write_g2o_file
+
+    fg2 = generators.manhattan_2d(generators.MC_BASE_SEED + 3, n_robots=3, n_steps=12)
+    fg3 = generators.grid_3d_factor_graph(generators.grid_3d_arrays(5, n_robots=2, n_steps=10, grid=6, n_landmarks=3, n_ranges=40))
+    for k, fg in enumerate((fg2, fg3)):
+        path = os.path.join(tmp_path, f"g{k}.g2o")
+        write_g2o_file(fg, path)
+        back = parse_g2o_file(path)
+        a, b = lower_factor_graph(fg), lower_factor_graph(back)
+        assert back.get_pose_chain_names() == fg.get_pose_chain_names()
+        for name in ("edge_i", "edge_j", "rng_a", "rng_b", "link_edge", "seg_ptr"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        for name in ("edge_k", "edge_tau", "rng_dist"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        assert np.allclose(a.edge_t, b.edge_t, rtol=0, atol=0) and np.allclose(a.rng_w, b.rng_w, rtol=1e-15)
+        assert np.allclose(a.edge_R, b.edge_R, rtol=0, atol=1e-15)  # 3D: through a unit quaternion
+    # plain integer ids and a standard landmark-free 2D file
+    path = os.path.join(tmp_path, "plain.g2o")
+    with open(path, "w") as f:
+        f.write("VERTEX_SE2 0 0 0 0\nVERTEX_SE2 1 1 0 0\nVERTEX_SE2 2 2 0 0.1\n")
+        f.write("EDGE_SE2 0 1 1 0 0 100 0 0 100 0 400\nEDGE_SE2 1 2 1 0 0.1 100 0 0 100 0 400\nEDGE_SE2 0 2 2 0 0.1 50 0 0 50 0 200\n")
+    fg = parse_g2o_file(path)
+    assert [p.name for p in fg.pose_variables[0]] == ["A0", "A1", "A2"]
+    assert len(fg.odom_measurements[0]) == 2 and len(fg.loop_closure_measurements) == 1
+    assert fg.loop_closure_measurements[0].translation_precision == 50 and fg.loop_closure_measurements[0].rotation_precision == 200
+    with open(path, "a") as f:
+        f.write("EDGE_BEARING 0 1 0.3 10\n")
+    with pytest.raises(ValueError):
+        parse_g2o_file(path)
