@@ -33,6 +33,14 @@ __device__ __forceinline__ double ls_candidate(int c) {
 // (shift 1), then 4096x (shift 2), ...
 __device__ __forceinline__ double ls_scale(int shift) { return ldexp(1.0, -6 * shift); }
 
+// 1 / x from the hardware seed (rcp.approx.ftz.f64, ~23 bits) and one Newton step (~46 bits): a handful of instructions
+// where the IEEE quotient is 20-30.  Used where the quotient feeds an iteration that corrects itself.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(fma(-x, r, 1.0), r, r);
+}
+
 // eps = 1 - rho*, the root in (0,1] of (q - 1 + e) e (2 - e) = kap (1 - e)   (stationarity of phi_mu in rho
 // with q = n / r, kap = mu / (w r^2)); parametrised by eps so that rho -> 1 keeps full relative accuracy.
 __device__ __forceinline__ double barrier_eps(double q, double kap) {
@@ -43,7 +51,7 @@ __device__ __forceinline__ double barrier_eps(double q, double kap) {
   for (int it = 0; it < 6; ++it) {  // quadratic convergence; most ranges need 1-3 steps
     const double F = (qm + e) * e * (2.0 - e) - kap * (1.0 - e);
     const double dF = e * (2.0 - e) + (qm + e) * (2.0 - 2.0 * e) + kap;
-    double ne = e - F / dF;
+    double ne = fma(-F, rcp_fast(dF), e);  // (the iteration's fixed point is the root whatever the quotient's last bits)
     if (!(ne > 0.0)) ne = 0.5 * e;
     ne = fmin(ne, 1.0);
     const bool done = fabs(ne - e) <= 2e-16 * e;
@@ -51,14 +59,6 @@ __device__ __forceinline__ double barrier_eps(double q, double kap) {
     if (done) break;
   }
   return e;
-}
-
-// 1 / x from the hardware seed (rcp.approx.ftz.f64, ~23 bits) and one Newton step (~46 bits): a handful of instructions
-// where the IEEE quotient is 20-30.  Used where the quotient feeds an iteration that corrects itself.
-__device__ __forceinline__ double rcp_fast(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  return fma(fma(-x, r, 1.0), r, r);
 }
 
 // The same root for G step sizes of one range at once (line search): the G Newton iterations are independent, so
