@@ -9,8 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscore_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "assemble.cuh", "precond.cuh", "coarse.cuh", "dense.cuh", "solver.cuh", "extract.cuh", "evaluate.cuh",
-           "../../include/score_b200.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + ["../../include/score_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
