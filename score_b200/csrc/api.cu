@@ -1589,15 +1589,19 @@ static int launch_cg_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
     if (pf) pf->mark(KI_COLPASS);
     n += launch_colpass(h, st, TM_CG);
   }
-  if (pf) pf->mark(KI_CTRL_A);
-  k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(Vc, h->T, h->st, cfg, h->W, TM_CG);
+  const bool own_alpha = h->V.mf && !dist;  // the element-wise update computes the step length itself: no controller launch
+  if (!own_alpha) {
+    if (pf) pf->mark(KI_CTRL_A);
+    k_ctrl_a<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(Vc, h->T, h->st, cfg, h->W, TM_CG);
+  }
   if (pf) pf->mark(KI_COLPASS);
   if (dist)
     launch_colapply(h, st, TM_CG);
   else if (h->V.mf)  // the operator was applied by k_hessvec: what is left of the column pass is element-wise
-    k_cg_update<<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->st, h->W);
+    k_cg_update<true><<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   else
     launch_colpass(h, st, TM_CG);
+  n -= own_alpha ? 1 : 0;
   n += 3 + launch_precond<D>(h, st, pf);
   if (pf) pf->mark(KI_CTRL_B);
   k_ctrl_b<<<wgrid(h, grid_for(P.n_inst, kSegThreads / 32), 16), kSegThreads, 0, st>>>(P, Vc, h->T, h->st, cfg, h->d_ndone, last ? TM_CG_LAST : TM_CG, h->W);

@@ -353,6 +353,11 @@ __device__ __forceinline__ double ctrl_sum(const double *part, int i0, int i1, i
   return warp_sum(acc);
 }
 
+// PCG step length rs / p'Hp (0: breakdown, the solve ends)
+__device__ __forceinline__ double cg_step_length(double pHp, double rs) {
+  return (pHp > 0.0 && pHp > 1e-30 * fabs(rs) && isfinite(pHp)) ? rs / pHp : 0.0;
+}
+
 // ---- ctrl_a: PCG step length / line-search decision / barrier update.  One warp per listed instance.
 __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstState *st, SolverCfg cfg, const int inst) {
   const int lane = threadIdx.x & 31;
@@ -363,13 +368,12 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
   if (phase == PH_CG) {
     const double pHp = V.mf ? ctrl_sum(V.part_hv, T.pb_begin[inst], T.pb_begin[inst + 1], 1, 0) : ctrl_sum(V.part_row, b0, b1, 1, 0);
     if (lane == 0) {
-      if (pHp > 0.0 && pHp > 1e-30 * fabs(S.rs) && isfinite(pHp)) {
-        S.alpha = S.rs / pHp;
-        S.dec += S.alpha * S.rs;  // -g.dz accumulates: Newton decrement^2 of the current solve
-      } else {
-        S.alpha = 0.0;
+      const double alpha = cg_step_length(pHp, S.rs);
+      S.alpha = alpha;
+      if (alpha != 0.0)
+        S.dec += alpha * S.rs;  // -g.dz accumulates: Newton decrement^2 of the current solve
+      else
         S.end_cg = 1;
-      }
     }
     return;
   }
@@ -794,15 +798,45 @@ __global__ void __launch_bounds__(kThreads) k_pupdate(SolverVecs V, BlockTables 
 constexpr int kVecChunk = 2048;  // doubles per chunk: kThreads threads x 4 double2
 
 // PH_CG (matrix-free operator): dz += alpha p ; r -= alpha h, h = 0 on the pinned pose's columns.
-__global__ void __launch_bounds__(kThreads) k_cg_update(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+// OWN_ALPHA (PCG ticks): there is no controller kernel between k_hessvec and this one — every CTA sums the instance's
+// p'Hp partials itself (warp 0, the controller's fixed order: the same bits in every CTA) and the CTA of chunk 0 records
+// the step length / Newton decrement / breakdown flag for the kernels that follow.  One launch less per PCG tick.
+template <bool OWN_ALPHA>
+__global__ void __launch_bounds__(kThreads) k_cg_update(DevProblem P, SolverVecs V, BlockTables T, InstState *st, WorkLists W) {
+  __shared__ double s_alpha;
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
+  if (OWN_ALPHA && blockIdx.x == 0 && threadIdx.x == 0) {  // (what k_ctrl_a does at this point of a tick)
+    const int q = (*W.par) ^ 1;
+    W.cnt[q * 3 + 0] = W.cnt[q * 3 + 1] = W.cnt[q * 3 + 2] = 0;
+  }
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxvc; item += gridDim.x) {
     const int inst = act[item / W.maxvc], chunk = (int)(item % W.maxvc);
     const int z0 = P.zoff[inst], n = P.zoff[inst + 1] - z0, c0 = chunk * kVecChunk;
     if (c0 >= n || st[inst].phase != PH_CG || st[inst].eval_now) continue;
-    const double alpha = st[inst].alpha;
+    double alpha;
+    if (OWN_ALPHA) {
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const double pHp = ctrl_sum(V.part_hv, T.pb_begin[inst], T.pb_begin[inst + 1], 1, 0);
+        if (threadIdx.x == 0) {
+          const double a = cg_step_length(pHp, st[inst].rs);
+          s_alpha = a;
+          if (chunk == 0) {
+            st[inst].alpha = a;
+            if (a != 0.0)
+              st[inst].dec += a * st[inst].rs;
+            else
+              st[inst].end_cg = 1;
+          }
+        }
+      }
+      __syncthreads();
+      alpha = s_alpha;
+    } else {
+      alpha = st[inst].alpha;
+    }
     const int c1 = min(n, c0 + kVecChunk), pin = P.blk;
     double *dz = V.dz + z0, *r = V.r + z0;
     const double *p = V.p + z0, *h = V.h + z0;
