@@ -119,6 +119,7 @@ struct ScoreHandle_ {
   cudaStream_t last_stream = nullptr;  // stream of the latest score_solve (a caller's stream, or own_stream)
   SolverCfg graph_cfg{};
   bool solved_once = false;
+  bool csr_valid = false;  // the reduced CSR pair is assembled (not the case after a matrix-free solve)
   int dist_per = 0;
 };
 
@@ -451,6 +452,8 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
     }
     case KI_ROWPASS:  // B (vals+cols+indptr), gather x; CG: w of the plain rows, u out, M_k of the ranges; LS: bdz out
       if (cg && D.mf) return 0.0;
+      if (ls && D.mf)  // k_rows_mf: x gathered, every factor once (measurement + 2 pose indices / 2 owner indices), bdz out
+        return 8.0 * nz + D.E * (8.0 * (d + d * d) + 8.0) + 8.0 * K + 8.0 * m;
       if (cg) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * (m - d * K) + 8.0 * m + 8.0 * K * d * (d + 1) / 2;
       if (ls) return 12.0 * nnz + 4.0 * (m + 1) + 8.0 * nz + 8.0 * m;
       return 0.0;
@@ -465,6 +468,9 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
                             : 0.0;
     case KI_COLPASS:  // B^T, gather u; CG: dz rw, p, r rw; LS: z rw, dz rw, r out; EVAL: z
       if (cg && D.mf) return 48.0 * nz;  // h, p in; dz, r read + written
+      if (D.mf)  // k_grad_mf: u in, incidence lists, measurements (base-pose role), then z / dz / r (LS) or z (EVAL)
+        return 8.0 * m + 4.0 * (Pn + D.L + 1) + 4.0 * Pn + 16.0 * (2.0 * K + D.Lp) + D.E * 8.0 * (d + d * d) +
+               (ls ? 40.0 : 8.0) * nz;
       if (cg || ls) return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
       return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * nz;
     case KI_PRECOND_REV:  // r, ytmp out, G, M
@@ -1219,6 +1225,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(V.part_col, cb.size() * 4)
   DA(V.h, P.nz)
   DA(V.part_hv, pb.size())
+  DA(V.part_gr, pb.size() * 4)
   P.n_inc = 2 * P.E + 2 * P.K + P.Lp;
   DA(P.inc_ptr, (size_t)P.P + P.L + 1)
   DA(P.inc_rec, P.n_inc)
@@ -1502,7 +1509,10 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
   const SolverVecs &Vc = dist ? h->Vg : h->V;  // what the controllers / coarse build read
   int n = 0;
   if (pf) pf->mark(KI_ROWPASS);
-  k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+  if (h->V.mf)  // bdz = B dz factor by factor
+    k_rows_mf<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W, RM_BDZ);
+  else
+    k_rowpass<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
   if (h->V.mf) {  // instances still inside a Newton solve take their PCG iteration matrix-free here as well
     if (pf) pf->mark(KI_HESSVEC);
     k_hessvec<D><<<wgrid(h, (long)P.n_inst * h->W.maxpb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
@@ -1534,7 +1544,15 @@ static int launch_ls_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t st
     for (int bi = 0; bi < (int)h->big.size(); ++bi) n += launch_coarse_big_build<D>(h, cfg, bi, st);
   }
   if (pf) pf->mark(KI_COLPASS);
-  n += launch_colpass(h, st, TM_LS);
+  if (h->V.mf) {
+    // gradient at the new point gathered from u factor by factor (+ the step itself); instances still inside a Newton
+    // solve take their PCG update (step length from k_ctrl_a above)
+    k_grad_mf<D><<<wgrid(h, (long)P.n_inst * h->W.maxpb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_LS, h->W);
+    k_cg_update<false><<<wgrid(h, (long)P.n_inst * h->W.maxvc, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, h->W);
+    n += 2;
+  } else {
+    n += launch_colpass(h, st, TM_LS);
+  }
   if (dist) {
     launch_colapply(h, st, TM_LS);
     n += 1;
@@ -1558,7 +1576,12 @@ static int launch_eval_tick(ScoreHandle_ *h, const SolverCfg &cfg, cudaStream_t 
   if (pf) pf->mark(KI_ROWUPDATE);
   k_rowupdate<D><<<wgrid(h, (long)P.n_inst * h->W.maxrb, 4), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
   if (pf) pf->mark(KI_COLPASS);
-  n += launch_colpass(h, st, TM_EVAL);
+  if (h->V.mf) {
+    k_grad_mf<D><<<wgrid(h, (long)P.n_inst * h->W.maxpb, 8), kThreads, 0, st>>>(P, h->V, h->T, h->st, TM_EVAL, h->W);
+    n += 1;
+  } else {
+    n += launch_colpass(h, st, TM_EVAL);
+  }
   if (dist) {
     launch_colapply(h, st, TM_EVAL);
     n += 1;
@@ -1680,6 +1703,34 @@ static int cycle_cg_ticks(int c, int base, int grow_after, int grow_every, int m
   return (int)std::min<long long>(n, max_cg);
 }
 
+// Reduced operator B (CSR) and its transpose from the factors (assemble.cuh + a stable radix sort by column).
+static int assemble_reduced(ScoreHandle_ *h, cudaStream_t st) {
+  DevProblem &P = h->P;
+  AsmOut out{P.indptr, P.cols, P.vals, P.w, P.b, h->nnz_row};
+  const long nf = (long)P.E + P.K + P.Lp;
+  k_assemble<<<grid_for(nf, 256), 256, 0, st>>>(P, ASM_REDUCED, 0, P.n_inst, out);
+  // transpose of the rows this rank owns (all rows on a single GPU): entries [nnz_lo, nnz_hi)
+  int nnz_lo = 0, nnz_hi = P.nnz;
+  if (h->n_ranks > 1) {
+    const int row_lo = h->W.rb_lo * kRowsPerBlock, row_hi = std::min(P.m, h->W.rb_hi * kRowsPerBlock);
+    SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_lo, P.indptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_hi, P.indptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  const int nloc = nnz_hi - nnz_lo;
+  k_iota<<<grid_for(std::max(nloc, 1), 256), 256, 0, st>>>(h->sort_idx, nloc);
+  int end_bit = 1;
+  while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
+  SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols + nnz_lo, h->sort_keys, h->sort_idx,
+                                                   h->sort_perm, nloc, 0, end_bit, st));
+  SCORE_CUDA_CHECK(cudaMemsetAsync(P.t_indptr, 0, sizeof(int) * (P.nz + 1), st));
+  if (nloc > 0)
+    k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->sort_keys, h->sort_perm, h->nnz_row + nnz_lo,
+                                                          P.vals + nnz_lo, P.t_indptr, P.t_rows, P.t_vals);
+  h->csr_valid = true;
+  return SCORE_OK;
+}
+
 extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats *stats, ScoreInstanceStats *inst_stats) {
   if (!h) {
     g_score_last_error = "null handle";
@@ -1738,30 +1789,17 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   h->last_stream = st;
   SCORE_CUDA_CHECK(cudaEventRecord(ev[0], st));
 
-  // ---- 1. assembly: reduced operator, its transpose
+  // ---- 1. assembly: reduced operator and its transpose (the matrix-free solve never reads them: built on demand by
+  //         score_get_csr), row weights, incidence lists of the factor-wise operator
   {
-    AsmOut out{P.indptr, P.cols, P.vals, P.w, P.b, h->nnz_row};
-    const long nf = (long)P.E + P.K + P.Lp;
-    k_assemble<<<grid_for(nf, 256), 256, 0, st>>>(P, ASM_REDUCED, 0, P.n_inst, out);
-    // transpose of the rows this rank owns (all rows on a single GPU): entries [nnz_lo, nnz_hi)
-    int nnz_lo = 0, nnz_hi = P.nnz;
-    if (h->n_ranks > 1) {
-      const int row_lo = h->W.rb_lo * kRowsPerBlock, row_hi = std::min(P.m, h->W.rb_hi * kRowsPerBlock);
-      SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_lo, P.indptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost, st));
-      SCORE_CUDA_CHECK(cudaMemcpyAsync(&nnz_hi, P.indptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost, st));
-      SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!mf) {
+      if ((rc = assemble_reduced(h, st))) return rc;
+      launches += 6;
+    } else {
+      h->csr_valid = false;
+      k_row_weights<<<grid_for((long)P.E + P.K + P.Lp, 256), 256, 0, st>>>(P, P.w, P.b);
+      launches += 1;
     }
-    const int nloc = nnz_hi - nnz_lo;
-    k_iota<<<grid_for(std::max(nloc, 1), 256), 256, 0, st>>>(h->sort_idx, nloc);
-    int end_bit = 1;
-    while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
-    SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols + nnz_lo, h->sort_keys,
-                                                     h->sort_idx, h->sort_perm, nloc, 0, end_bit, st));
-    SCORE_CUDA_CHECK(cudaMemsetAsync(P.t_indptr, 0, sizeof(int) * (P.nz + 1), st));
-    if (nloc > 0)
-      k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->sort_keys, h->sort_perm, h->nnz_row + nnz_lo,
-                                                            P.vals + nnz_lo, P.t_indptr, P.t_rows, P.t_vals);
-    launches += 6;
     if (P.n_inc > 0) {
       // incidence lists of the matrix-free operator: (owner, factor) pairs in factor order, stable sort by owner
       // (the transpose's index scratch is free again)
@@ -1780,7 +1818,10 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
   // ---- 2. preconditioner, start point, solver state
   {
     k_dead_reckon<<<grid_for(P.n_seg, 64), 64, 0, st>>>(P);
-    k_diag_setup<<<grid_for((long)P.P + (long)P.L * d, 256), 256, 0, st>>>(P, h->wsum);
+    if (mf)
+      k_diag_setup_mf<<<grid_for((long)P.P + P.L, 256), 256, 0, st>>>(P, h->wsum);
+    else
+      k_diag_setup<<<grid_for((long)P.P + (long)P.L * d, 256), 256, 0, st>>>(P, h->wsum);
     if (h->n_ranks > 1) {  // range weights were summed over the local rows only
       g_nccl.AllReduce(h->wsum, h->wsum, P.P, ncclDouble, ncclSum, h->comm, st);
       if (P.L > 0) g_nccl.AllReduce(P.lm_inv, P.lm_inv, (size_t)P.L * d, ncclDouble, ncclSum, h->comm, st);
@@ -1788,7 +1829,12 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     if (P.L > 0) k_lm_finish<<<grid_for((long)P.L * d, 256), 256, 0, st>>>(P);
     k_build_M<<<grid_for(P.P, 128), 128, 0, st>>>(P, h->wsum);
     k_init_z<<<grid_for(P.nz, 256), 256, 0, st>>>(P, V.z);
-    k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
+    if (!mf)
+      k_residual<<<grid_for(P.m, kThreads), kThreads, 0, st>>>(P, V.z, V.res);
+    else if (d == 2)
+      k_rows_mf_all<2><<<std::max(1, std::min(h->T.n_rb, h->n_sm * 16)), kThreads, 0, st>>>(P, V, h->T, h->st, RM_RES);
+    else
+      k_rows_mf_all<3><<<std::max(1, std::min(h->T.n_rb, h->n_sm * 16)), kThreads, 0, st>>>(P, V, h->T, h->st, RM_RES);
     if ((h->c_nmax > 0 || !h->big.empty()) && std::max(P.c_ninc, P.c_npair) > 0) {
       if (d == 2)
         k_coarse_static<2><<<grid_for(std::max(P.c_ninc, P.c_npair), 256), 256, 0, st>>>(P);
@@ -2130,6 +2176,11 @@ extern "C" int score_get_csr(ScoreHandle h, int32_t which, int32_t inst, int64_t
   if (!h->solved_once) {
     g_score_last_error = "the reduced operator exists only after score_solve";
     return SCORE_ERR_STATE;
+  }
+  if (!h->csr_valid) {  // a matrix-free solve does not assemble the pair: do it now
+    int rc = assemble_reduced(h, h->own_stream);
+    if (rc) return rc;
+    SCORE_CUDA_CHECK(cudaStreamSynchronize(h->own_stream));
   }
   const int rows = h->roff[inst + 1] - h->roff[inst], cols = h->zoff[inst + 1] - h->zoff[inst];
   const int nn = h->nnzoff[inst + 1] - h->nnzoff[inst];

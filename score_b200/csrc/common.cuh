@@ -45,6 +45,7 @@ struct InstState {
   double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
   double mu_out;                           // barrier parameter of the auxiliary variables the last certificate was taken with
+  double dec_prev;                         // Newton decrement^2 of the previous step of this barrier stage (0: first step)
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
 };
 
@@ -115,6 +116,7 @@ struct SolverVecs {
   // matrix-free PCG operator (hessvec.cuh): h = B^T H_r B p and the partial p'Hp of every pose / landmark block
   double *h;         // [nz]
   double *part_hv;   // [n_pose_blocks]
+  double *part_gr;   // [n_pose_blocks * 4] certificate sums |g|^2, g.z, |z|^2 of the matrix-free gradient kernel
   int mf, pad1;      // 1: PCG iterations apply the operator factor by factor; 0: assembled CSR pair (row + column pass)
   // diagnostic trace (ScoreParams.verbose >= 2): per instance kTraceRec doubles per Newton step, trace_cap steps
   double *trace;

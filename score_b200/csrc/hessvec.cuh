@@ -360,6 +360,275 @@ __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTa
   if (tid == 0) V.part_hv[bid] = qtot;
 }
 
+// ---- The line-search ticks' two operator applications, factor by factor as well -----------------------------------
+// (1) rows: out = B x (- b) for the rows of one row block — bdz = B dz before the line search, res = B z - b at the
+//     start — one thread per factor, the factor's rows in the reference's order (assemble.cuh).
+// (2) gradient: h = B^T u gathered per pose / landmark from the row-space vector u = dF/d(res) that k_rowupdate wrote,
+//     fused with what the column pass did with it (new point z += step dz, dz = 0, r = -h; or the certificate's sums).
+// With these the assembled CSR pair is not touched by a matrix-free solve at all (it is still built for
+// score_get_csr, for operator_mode = 1 and for the row-partitioned multi-GPU solve).
+enum RowsMode : int { RM_BDZ = 0, RM_RES = 1 };
+
+template <int D>
+__device__ __forceinline__ void rows_mf_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid,
+                                             const int mode) {
+  constexpr int D1 = D + 1, BLK = D * D1, RPE = D + D * D;
+  const BlockDesc bd = T.rb[bid];
+  const int inst = bd.inst;
+  if (mode == RM_BDZ && (st[inst].phase != PH_LS || st[inst].skip_ls || st[inst].eval_now)) return;
+  const double *xz = (mode == RM_BDZ ? V.dz : V.z) + P.zoff[inst];
+  double *out = mode == RM_BDZ ? V.bdz : V.res;
+  const int r0 = P.roff[inst], e0 = P.edge_off[inst], Ei = P.edge_off[inst + 1] - e0;
+  const int k0 = P.rng_off[inst], Ki = P.rng_off[inst + 1] - k0, q0 = P.prior_off[inst];
+  const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
+  const int rr0 = r0 + Ei * RPE, rp0 = rr0 + Ki * D;
+  // relative-pose factors whose rows lie in this block (kRowsPerBlock is a multiple of the rows per factor)
+  {
+    const int a = max(bd.i0, r0), b = min(bd.i1, rr0);
+    for (int el = (a - r0) / RPE + threadIdx.x; el < (b - r0) / RPE; el += kThreads) {
+      const int e = e0 + el;
+      double xi[BLK], xj[BLK], tm[D], Rm[D * D], k2, tau2;
+      load_pose<D>(xz, 0, P.edge_i[e], xi);
+      load_pose<D>(xz, 0, P.edge_j[e], xj);
+      load_edge<D>(P, e, tm, Rm, k2, tau2);
+      double *o = out + r0 + (size_t)el * RPE;
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        double qt = xj[r * D1 + D] - xi[r * D1 + D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) qt -= xi[r * D1 + c] * tm[c];
+        o[r] = qt;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double qr = xj[r * D1 + c];
+#pragma unroll
+          for (int m = 0; m < D; ++m) qr -= xi[r * D1 + m] * Rm[m * D + c];
+          o[D + r * D + c] = qr;
+        }
+      }
+    }
+  }
+  {  // range terms: rows t_a - t_b
+    const int a = max(bd.i0, rr0), b = min(bd.i1, rp0);
+    for (int kl = (a - rr0) / D + threadIdx.x; kl < (b - rr0) / D; kl += kThreads) {
+      const int k = k0 + kl;
+      double ta[D], tb[D];
+      load_trans<D>(xz, 0, Pi, P.rng_a[k], ta);
+      load_trans<D>(xz, 0, Pi, P.rng_b[k], tb);
+#pragma unroll
+      for (int r = 0; r < D; ++r) out[rr0 + (size_t)kl * D + r] = ta[r] - tb[r];
+    }
+  }
+  {  // landmark priors: rows l - prior
+    const int a = max(bd.i0, rp0), b = bd.i1;
+    for (int ql = (a - rp0) / D + threadIdx.x; ql < (b - rp0) / D; ql += kThreads) {
+      const int q = q0 + ql, lq = P.prior_l[q];
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+        out[rp0 + (size_t)ql * D + r] = xz[Pi * BLK + lq * D + r] - (mode == RM_RES ? P.prior_t[(size_t)q * D + r] : 0.0);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_rows_mf(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W,
+                                                     int mode) {
+  const int *act;
+  int n_act;
+  wl_get(W, WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxrb; item += gridDim.x) {
+    const int inst = act[item / W.maxrb], bid = T.rb_begin[inst] + (int)(item % W.maxrb);
+    if (bid < T.rb_begin[inst + 1]) rows_mf_body<D>(P, V, T, st, bid, mode);
+  }
+}
+
+// the same over every row block of the batch (initial residual: no work lists yet)
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_rows_mf_all(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, int mode) {
+  for (int bid = blockIdx.x; bid < T.n_rb; bid += gridDim.x) rows_mf_body<D>(P, V, T, st, bid, mode);
+}
+
+// weights and right-hand sides of the rows (what the assembly writes beside the matrix)
+__global__ void k_row_weights(DevProblem P, double *__restrict__ w, double *__restrict__ b) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = P.d, rpe = P.rpe;
+  if (t < P.E) {
+    const int e = (int)t, inst = find_inst(P.edge_off, P.n_inst, e);
+    const int row = P.roff[inst] + (e - P.edge_off[inst]) * rpe;
+    for (int r = 0; r < rpe; ++r) {
+      w[row + r] = r < d ? P.edge_k[e] : P.edge_tau[e];
+      b[row + r] = 0.0;
+    }
+  } else if (t < (long)P.E + P.K) {
+    const int k = (int)(t - P.E), inst = find_inst(P.rng_off, P.n_inst, k);
+    const int row = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * rpe + (k - P.rng_off[inst]) * d;
+    for (int r = 0; r < d; ++r) {
+      w[row + r] = P.rng_w[k];
+      b[row + r] = 0.0;
+    }
+  } else if (t < (long)P.E + P.K + P.Lp) {
+    const int q = (int)(t - P.E - P.K), inst = find_inst(P.prior_off, P.n_inst, q);
+    const int row = P.roff[inst] + (P.edge_off[inst + 1] - P.edge_off[inst]) * rpe +
+                    (P.rng_off[inst + 1] - P.rng_off[inst]) * d + (q - P.prior_off[inst]) * d;
+    for (int r = 0; r < d; ++r) {
+      w[row + r] = P.prior_w[q];
+      b[row + r] = P.prior_t[(size_t)q * d + r];
+    }
+  }
+}
+
+// range weight incident on every pose translation / inverse Hessian diagonal of every landmark coordinate from the
+// incidence lists (the matrix-free twin of k_diag_setup; k_lm_finish inverts lm_inv afterwards)
+__global__ void k_diag_setup_mf(DevProblem P, double *wsum) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= P.P + P.L) return;
+  double acc = 0.0;
+  for (int j = P.inc_ptr[o]; j < P.inc_ptr[o + 1]; ++j) {
+    const IncRec rec = P.inc_rec[j];
+    const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
+    if (kind == INC_RA || kind == INC_RB)
+      acc += P.rng_w[id];
+    else if (kind == INC_PR)
+      acc += P.prior_w[id];
+  }
+  if (o < P.P) {
+    wsum[o] = acc;
+  } else {
+    for (int r = 0; r < P.d; ++r) P.lm_inv[(size_t)(o - P.P) * P.d + r] = acc;
+  }
+}
+
+// h = B^T u per pose / landmark, then the column-space update of the tick.  mode TM_LS: instances in PH_LS take the
+// step (z += step dz, dz = 0, r = -h).  mode TM_EVAL: partial |g|^2, g.z, |z|^2 of the instances being certified.
+template <int D>
+__device__ __forceinline__ void grad_mf_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid,
+                                             const int mode) {
+  constexpr int D1 = D + 1, BLK = D * D1, RPE = D + D * D;
+  __shared__ double red[16 * (kThreads / 32)];
+  const HvBlock bd = T.pb[bid];
+  const int inst = bd.inst;
+  const bool eval = mode == TM_EVAL;
+  const int phase = st[inst].phase;
+  if (phase == PH_DONE) return;
+  if (eval ? !st[inst].eval_now : (phase != PH_LS || st[inst].eval_now)) return;
+  const int z0 = bd.z0, Pi = bd.Pi;
+  const int r0 = P.roff[inst], e0 = P.edge_off[inst], Ei = P.edge_off[inst + 1] - e0;
+  const int k0 = P.rng_off[inst], Ki = P.rng_off[inst + 1] - k0, q0 = P.prior_off[inst];
+  const int rr0 = r0 + Ei * RPE, rp0 = rr0 + Ki * D;
+  const double *u = V.u;
+  const IncRec *__restrict__ recs = reinterpret_cast<const IncRec *>(P.inc_rec);
+  const double step = st[inst].step;
+  const int tid = threadIdx.x;
+  double gg = 0.0, gz = 0.0, zz = 0.0;
+  auto finish = [&](int col, double h) {  // one column: certificate sums, or the step to the new point
+    if (col < P.blk) h = 0.0;  // pinned pose
+    double *zc = V.z + z0 + col;
+    if (eval) {
+      const double zv = *zc;
+      gg += h * h;
+      gz += h * zv;
+      zz += zv * zv;
+    } else {
+      double *dzc = V.dz + z0 + col;
+      *zc = fma(step, *dzc, *zc);
+      *dzc = 0.0;
+      V.r[z0 + col] = -h;
+    }
+  };
+  if (bd.kind == CB_POSE) {
+    const int p = bd.i0 + tid;
+    if (p < bd.i1) {
+      const int pg = bd.pg0 + p;
+      double h[BLK];
+#pragma unroll
+      for (int i = 0; i < BLK; ++i) h[i] = 0.0;
+      // rows of a relative-pose factor: d translation rows, then d x d rotation rows
+      auto edge_rows = [&](int e, bool at_j) {
+        const double *ue = u + r0 + (size_t)(e - e0) * RPE;
+        if (at_j) {
+#pragma unroll
+          for (int r = 0; r < D; ++r) {
+            h[r * D1 + D] += ue[r];
+#pragma unroll
+            for (int c = 0; c < D; ++c) h[r * D1 + c] += ue[D + r * D + c];
+          }
+        } else {
+          double tm[D], Rm[D * D], k2, tau2;
+          load_edge<D>(P, e, tm, Rm, k2, tau2);
+#pragma unroll
+          for (int r = 0; r < D; ++r) {
+            h[r * D1 + D] -= ue[r];
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+              double acc = ue[r] * tm[m];
+#pragma unroll
+              for (int c = 0; c < D; ++c) acc += ue[D + r * D + c] * Rm[m * D + c];
+              h[r * D1 + m] -= acc;
+            }
+          }
+        }
+      };
+      const int e_in = P.link_edge[pg], e_out = (p + 1 < Pi) ? P.link_edge[pg + 1] : -1;
+      if (e_in >= 0) edge_rows(e_in, true);
+      if (e_out >= 0) edge_rows(e_out, false);
+      for (int j = P.inc_ptr[pg]; j < P.inc_ptr[pg + 1]; ++j) {
+        const IncRec rec = recs[j];
+        const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
+        if (kind == INC_RA || kind == INC_RB) {
+          const double *uk = u + rr0 + (size_t)(id - k0) * D;
+#pragma unroll
+          for (int r = 0; r < D; ++r) h[r * D1 + D] += (kind == INC_RA) ? uk[r] : -uk[r];
+        } else if (kind == INC_EJ) {
+          edge_rows(id, true);
+        } else if (kind == INC_EI) {
+          edge_rows(id, false);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BLK; ++i) finish(p * BLK + i, h[i]);
+    }
+  } else {
+    for (int q = bd.i0; q < bd.i1; ++q) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.0;
+      const int j0 = P.inc_ptr[P.P + bd.lg0 + q], j1 = P.inc_ptr[P.P + bd.lg0 + q + 1];
+      for (int j = j0 + tid; j < j1; j += kThreads) {
+        const IncRec rec = recs[j];
+        const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
+        const double *uk = (kind == INC_PR) ? u + rp0 + (size_t)(id - q0) * D : u + rr0 + (size_t)(id - k0) * D;
+#pragma unroll
+        for (int r = 0; r < D; ++r) v[r] += (kind == INC_RB) ? -uk[r] : uk[r];
+      }
+      const double tot = block_sum16<kThreads>(v, red);  // thread i < 16 holds the total of v[i]
+      if (tid < D) finish(Pi * BLK + q * D + tid, tot);
+    }
+  }
+  if (eval) {
+    const double a = block_sum<kThreads>(gg, red);
+    const double b = block_sum<kThreads>(gz, red);
+    const double c = block_sum<kThreads>(zz, red);
+    if (tid == 0) {
+      V.part_gr[(size_t)bid * 4 + 0] = a;
+      V.part_gr[(size_t)bid * 4 + 1] = b;
+      V.part_gr[(size_t)bid * 4 + 2] = c;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_grad_mf(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, int mode,
+                                                     WorkLists W) {
+  const int *act;
+  int n_act;
+  wl_get(W, mode == TM_EVAL ? WL_EVAL : WL_RUN, act, n_act);
+  for (long long item = blockIdx.x; item < (long long)n_act * W.maxpb; item += gridDim.x) {
+    const int inst = act[item / W.maxpb], bid = T.pb_begin[inst] + (int)(item % W.maxpb);
+    if (bid < T.pb_begin[inst + 1]) grad_mf_body<D>(P, V, T, st, bid, mode);
+    __syncthreads();
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads, 4) k_hessvec(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
   const int *act;

@@ -413,13 +413,17 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
     const double ctol = (S.mu <= cfg.mu_eval) ? cfg.center_tol_late : cfg.center_tol;
     const bool retry = step == 0.0 && lam2 > ctol && S.ls_shift < 3;
     S.ls_shift = retry ? S.ls_shift + 1 : 0;
-    // a decrement at the resolution of F_mu itself cannot be driven lower: the stage is as centred as it gets
-    const bool at_floor = S.mu <= cfg.mu_eval && S.dec <= 1e-11 * (1.0 + fabs(best));
+    // a decrement that has stopped falling near the resolution of F_mu cannot be driven lower: the stage is as centred
+    // as it gets.  (Judged by stagnation, not by a fixed level: the certificate's gap term g.z is bounded by
+    // sqrt(decrement * z'Hz), so every further decade the Newton iteration still delivers is needed.)
+    const bool at_floor = S.mu <= cfg.mu_eval && S.dec <= 1e-9 * (1.0 + fabs(best)) && S.dec_prev > 0.0 && S.dec > 0.5 * S.dec_prev;
+    const double mu_before = S.mu;
     if (S.mu > 0.0 && !retry && (lam2 <= ctol || at_floor || step == 0.0)) {
       if (S.mu <= cfg.mu_eval) S.want_eval = 1;
       if (S.mu <= cfg.mu_min) S.stall += 1;
       S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
     }
+    S.dec_prev = (S.mu != mu_before) ? 0.0 : S.dec;
     if (S.mu == 0.0) S.want_eval = 1;
     // long late stages: look at the true certificate every 4th Newton step as well
     if (S.mu <= cfg.mu_eval && (S.newton_it & 3) == 3) S.want_eval = 1;
@@ -649,9 +653,12 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
     const double dn2 = ctrl_sum(V.part_upd, rb0, rb1, 4, 1);
     const double gsum = ctrl_sum(V.part_upd, rb0, rb1, 4, 2);
     const double ssum = ctrl_sum(V.part_upd, rb0, rb1, 4, 3);
-    const double gg = ctrl_sum(V.part_col, cb0, cb1, 4, 0);
-    const double gz = ctrl_sum(V.part_col, cb0, cb1, 4, 1);
-    const double zz = ctrl_sum(V.part_col, cb0, cb1, 4, 2);
+    // (matrix-free solve: the gradient kernel's sums per pose / landmark block)
+    const double *pc = V.mf ? V.part_gr : V.part_col;
+    const int c0 = V.mf ? T.pb_begin[inst] : cb0, c1 = V.mf ? T.pb_begin[inst + 1] : cb1;
+    const double gg = ctrl_sum(pc, c0, c1, 4, 0);
+    const double gz = ctrl_sum(pc, c0, c1, 4, 1);
+    const double zz = ctrl_sum(pc, c0, c1, 4, 2);
     if (lane != 0) return;
     // SURVEY.md App. A.7 at x = (z, delta): r_stat = ||x - proj_C(x - g)|| / (1 + ||x||) with min(lambda, s) per range in
     // the delta block; p - D = g_free . z + sum lambda s
