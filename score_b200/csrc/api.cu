@@ -76,7 +76,9 @@ struct ScoreHandle_ {
   double *wsum = nullptr;
   int *nnz_row = nullptr;
   // transpose scratch
-  int *sort_keys = nullptr, *sort_idx = nullptr, *sort_perm = nullptr;
+  int *sort_keys = nullptr, *sort_idx = nullptr;                       // incidence-list sort
+  int *csr_keys = nullptr, *csr_idx = nullptr, *csr_perm = nullptr;    // transpose sort (allocated with the CSR pair)
+  size_t sort_cap = 0;  // entries of sort_keys / sort_idx
   void *sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   // outputs
@@ -902,7 +904,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   SCORE_CUDA_CHECK(cudaSetDevice(device));
   h->device = device;
   // footprint estimate for the first arena chunk: operator in both orientations + sort scratch + solver vectors
-  h->arena_hint = (size_t)(40 * nnz + 60 * nz + 40 * m) + (1u << 20);
+  h->arena_hint = (size_t)(90 * nz + 60 * m + 40 * (2 * desc->E + 2 * desc->K)) + (1u << 20);
   DevProblem &P = h->P;
   P.d = d;
   P.blk = (int)blk;
@@ -1047,22 +1049,17 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
 #undef UP
 #define DA(ptr, n) \
   if ((rc = dalloc(h, &(ptr), (size_t)(n)))) return rc;
-  DA(P.indptr, P.m + 1)
-  DA(P.cols, P.nnz)
-  DA(P.vals, P.nnz)
-  DA(P.t_indptr, P.nz + 1)
-  DA(P.t_rows, P.nnz)
-  DA(P.t_vals, P.nnz)
   DA(P.w, P.m)
   DA(P.b, P.m)
   DA(P.G, (size_t)P.P * blk)
   DA(P.M, (size_t)P.P * (d + 1) * (d + 1))
   DA(P.lm_inv, (size_t)P.L * d)
   DA(h->wsum, P.P)
-  DA(h->nnz_row, P.nnz)
-  DA(h->sort_keys, P.nnz)
-  DA(h->sort_idx, P.nnz)
-  DA(h->sort_perm, P.nnz)
+  // index scratch of the incidence-list sort; the assembled CSR pair and its sort scratch are allocated on first use
+  // (assemble_reduced): a matrix-free solve never needs them — 40 bytes per stored entry, ~2/3 of a handle's footprint
+  h->sort_cap = (size_t)std::max<long long>(1, 2 * desc->E + 2 * desc->K + desc->Lp);
+  DA(h->sort_keys, h->sort_cap)
+  DA(h->sort_idx, h->sort_cap)
   SolverVecs &V = h->V;
   DA(V.z, P.nz)
   DA(V.dz, P.nz)
@@ -1244,30 +1241,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   if (!h->h_ndone) SCORE_CUDA_CHECK(cudaMallocHost((void **)&h->h_ndone, 2 * sizeof(int)));
   for (auto &e : h->ev_done) SCORE_CUDA_CHECK(g_cache.get_event(device, &e));
   trace.mark("block-tables+allocs");
-  // radix-sort scratch for the transpose
-  int end_bit = 1;
-  while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
-  {
-    // the size query walks through the runtime (device / kernel attribute look-ups); cache it per (nnz, end_bit)
-    static std::mutex mu;
-    static std::map<std::pair<long long, int>, size_t> known;
-    std::lock_guard<std::mutex> lk(mu);
-    const auto key = std::make_pair((long long)P.nnz, end_bit);
-    auto it = known.find(key);
-    if (it == known.end()) {
-      size_t bytes = 0;
-      SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, P.cols, h->sort_keys, h->sort_idx, h->sort_perm,
-                                                       P.nnz, 0, end_bit, (cudaStream_t)0));
-      it = known.emplace(key, bytes).first;
-    }
-    h->sort_tmp_bytes = it->second;
-  }
-  {
-    char *tmp = nullptr;
-    if ((rc = dalloc(h, &tmp, h->sort_tmp_bytes))) return rc;
-    h->sort_tmp = tmp;
-  }
-  if (P.n_inc > 0) {  // the same for the incidence lists of the matrix-free operator (keys: owners)
+  if (P.n_inc > 0) {  // radix-sort scratch of the incidence lists of the matrix-free operator (keys: owners)
     int ob = 1;
     while ((1ll << ob) <= (long long)P.P + P.L + 1) ++ob;  // owners 0 .. P + L (the last one: the odometry-link sentinel)
     static std::mutex mu;
@@ -1706,6 +1680,39 @@ static int cycle_cg_ticks(int c, int base, int grow_after, int grow_every, int m
 // Reduced operator B (CSR) and its transpose from the factors (assemble.cuh + a stable radix sort by column).
 static int assemble_reduced(ScoreHandle_ *h, cudaStream_t st) {
   DevProblem &P = h->P;
+  int end_bit = 1;
+  while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
+  if (!P.indptr) {  // first use: the pair, the transpose's scratch (arena: stream-ordered, synchronised by get_chunk)
+    int rc;
+    if ((rc = dalloc(h, &P.indptr, (size_t)P.m + 1))) return rc;
+    if ((rc = dalloc(h, &P.cols, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &P.vals, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &P.t_indptr, (size_t)P.nz + 1))) return rc;
+    if ((rc = dalloc(h, &P.t_rows, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &P.t_vals, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &h->nnz_row, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &h->csr_keys, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &h->csr_idx, (size_t)P.nnz))) return rc;
+    if ((rc = dalloc(h, &h->csr_perm, (size_t)P.nnz))) return rc;
+    {
+      // the size query walks through the runtime (device / kernel attribute look-ups); cache it per (nnz, end_bit)
+      static std::mutex mu;
+      static std::map<std::pair<long long, int>, size_t> known;
+      std::lock_guard<std::mutex> lk(mu);
+      const auto key = std::make_pair((long long)P.nnz, end_bit);
+      auto it = known.find(key);
+      if (it == known.end()) {
+        size_t bytes = 0;
+        SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, P.cols, h->csr_keys, h->csr_idx, h->csr_perm, P.nnz, 0,
+                                                         end_bit, (cudaStream_t)0));
+        it = known.emplace(key, bytes).first;
+      }
+      h->sort_tmp_bytes = it->second;
+    }
+    char *tmp = nullptr;
+    if ((rc = dalloc(h, &tmp, h->sort_tmp_bytes))) return rc;
+    h->sort_tmp = tmp;
+  }
   AsmOut out{P.indptr, P.cols, P.vals, P.w, P.b, h->nnz_row};
   const long nf = (long)P.E + P.K + P.Lp;
   k_assemble<<<grid_for(nf, 256), 256, 0, st>>>(P, ASM_REDUCED, 0, P.n_inst, out);
@@ -1718,14 +1725,12 @@ static int assemble_reduced(ScoreHandle_ *h, cudaStream_t st) {
     SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   const int nloc = nnz_hi - nnz_lo;
-  k_iota<<<grid_for(std::max(nloc, 1), 256), 256, 0, st>>>(h->sort_idx, nloc);
-  int end_bit = 1;
-  while ((1ll << end_bit) <= (long long)P.nz) ++end_bit;
-  SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols + nnz_lo, h->sort_keys, h->sort_idx,
-                                                   h->sort_perm, nloc, 0, end_bit, st));
+  k_iota<<<grid_for(std::max(nloc, 1), 256), 256, 0, st>>>(h->csr_idx, nloc);
+  SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, P.cols + nnz_lo, h->csr_keys, h->csr_idx,
+                                                   h->csr_perm, nloc, 0, end_bit, st));
   SCORE_CUDA_CHECK(cudaMemsetAsync(P.t_indptr, 0, sizeof(int) * (P.nz + 1), st));
   if (nloc > 0)
-    k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->sort_keys, h->sort_perm, h->nnz_row + nnz_lo,
+    k_transpose_fill<<<grid_for(nloc, 256), 256, 0, st>>>(nloc, P.nz, h->csr_keys, h->csr_perm, h->nnz_row + nnz_lo,
                                                           P.vals + nnz_lo, P.t_indptr, P.t_rows, P.t_vals);
   h->csr_valid = true;
   return SCORE_OK;
