@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2, help="sub-batches per GPU solved concurrently on their own streams")
     ap.add_argument("--parts", type=int, default=0, help="sub-batches per GPU (default: --streams); more parts than "
                     "streams staggers them so that one sub-batch's sparse tail runs under the next one's dense start")
-    ap.add_argument("--sets", type=int, default=2, help="handle sets the timed steps are double-buffered over: sets x parts "
+    ap.add_argument("--sets", type=int, default=3, help="handle sets the timed steps are double-buffered over: sets x parts "
                     "sub-batch solves are in flight (the sparse last cycles of some run under the dense first cycles of others)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --instances per GPU (the default, BASELINE configs[3] per GPU); strong: --instances in total, "
@@ -635,7 +635,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         solver.close()
         g2 = ScoreSolverGroup(prob_pinned, n_streams=args.streams, device=local_rank, create=False, n_parts=args.parts)
         g2.prewarm()  # the library's memory / stream caches then hold a spare set of handle resources
-        inflight = args.streams * args.sets
+        inflight = min(4, args.streams * args.sets)  # sub-batch solves in flight (more only adds host-side contention)
         g2.prewarm(extra=inflight - args.streams)
         g2.run_pipelined(out=outs, steps=2, inflight=inflight, kkt_tol=KKT_TOL)  # same queue depth as the timed run
         barrier()
