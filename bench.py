@@ -62,6 +62,10 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --instances per GPU (the default, BASELINE configs[3] per GPU); strong: --instances in total, "
                     "split over the ranks")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "static", "dynamic"],
+                    help="N > 1: static = every rank re-solves its own shard; dynamic = the sub-batch jobs of all ranks form "
+                    "one queue that the ranks drain together (sharding.SweepQueue; every rank holds all sub-batches). "
+                    "auto: dynamic when N > 1")
     ap.add_argument("--no-per-config", action="store_true", help="skip the single-graph time-to-solve table")
     ap.add_argument("--no-config5", action="store_true", help="skip the large 3D graph in the per-config table")
     ap.add_argument("--parity-kkt", type=int, default=4, help="instances of the parity sample whose GPU solution is "
@@ -225,6 +229,11 @@ def workload_config(args, sample_note=None):
         "pipelined per sub-batch (no barrier between steps, sub-batches half a solve out of phase: the sparse last cycles "
         "of one sub-batch run under the dense first cycles of the other); all K steps start and end inside the timed region",
     }
+    if getattr(args, "dynamic", False):
+        cfg["schedule"] = ("dynamic: the sub-batch jobs of all ranks and all K steps form ONE queue (longest sub-batch first "
+                           "inside a step); every rank holds every sub-batch resident and claims the next job from a counter in "
+                           "the process group's key-value store (no data-path collective), so a rank that drew an "
+                           "ill-conditioned sub-batch claims fewer jobs instead of holding the step back")
     if sample_note:
         cfg["reference_sample"] = sample_note
     return cfg
@@ -399,54 +408,92 @@ def run_gpu_arm(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream().cuda_stream
-    # the batch is split into `--streams` sub-batches, each on its own CUDA stream and host thread
-    group = ScoreSolverGroup(prob, n_streams=args.streams, device=local_rank, n_parts=args.parts)
+    args.dynamic = world > 1 and args.schedule in ("auto", "dynamic")
+    n_parts_rank = max(1, min(args.parts or args.streams, n_local))
+    inflight_dev = args.streams * args.sets  # sub-batch solves in flight per GPU (both schedules)
 
-    # warm-up and timed region both run the steps as a pipeline (ScoreSolverGroup.solve_steps): every sub-batch is
-    # re-solved step after step by its own host thread, the sub-batches half a solve out of phase, so that the sparse
-    # last cycles of one (a few ill-conditioned instances) run under the dense first cycles of the other.  All K steps
-    # start and finish inside the timed region.
-    group.solve(kkt_tol=KKT_TOL)
-    group.solve_steps(max(args.sets, args.warmup), n_sets=args.sets, kkt_tol=KKT_TOL)
-    barrier()
+    def split(p, n):
+        from score_b200.lowering import slice_instances
+
+        cuts = [round(j * p.n_instances / n) for j in range(n + 1)]
+        return [slice_instances(p, cuts[j], cuts[j + 1]) for j in range(n)]
+
+    def run_dynamic(parts_global, steps, warm_steps):
+        """K steps over the sub-batches of ALL ranks as one queue (device-resident handles on every rank)."""
+        from score_b200.sharding import JobCounter, SweepQueue
+        from score_b200.solver import HandlePool
+
+        run_dynamic.calls = getattr(run_dynamic, "calls", 0) + 1
+        counter = JobCounter(dist.distributed_c10d._get_default_store(), key=f"score_b200/bench/{run_dynamic.calls}")
+        with HandlePool(parts_global, device=local_rank, copies=2) as pool:
+            costs = [float(w.cycles) for w in pool.warm(kkt_tol=KKT_TOL)]  # deterministic: the same on every rank
+            with SweepQueue(len(parts_global), lambda step, part, w: pool.solve(part, kkt_tol=KKT_TOL), counter,
+                            inflight=inflight_dev) as q:
+                q.run(warm_steps, costs)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res = q.run(steps, costs)  # returns after this rank's last job
+                e1.record()
+                barrier()
+        return e0.elapsed_time(e1), [r[2] for r in res], costs
+
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    bytes_total = 0.0
-    solve_ms = 0.0
-    ticks = 0
-    cycles = 0
-    n_solved = 0
-    ev0.record()
-    for st in group.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL):  # returns after the last solve of the last step
-        launches += st.kernel_launches
-        bytes_total += st.algorithmic_bytes
-        solve_ms += st.solve_ms
-        ticks += st.ticks
-        cycles += st.cycles
-        n_solved += st.n_solved
-    ev1.record()
-    barrier()
+    parts_global = None
+    if args.dynamic:
+        shards = [None] * world
+        dist.all_gather_object(shards, prob)  # ~0.2 MB of lowered arrays per instance
+        parts_global = [pt for sh in shards for pt in split(sh, n_parts_rank)]
+        del shards
+        sampler.start()
+        elapsed, sts, costs_global = run_dynamic(parts_global, args.steps, max(1, args.warmup))
+        group = None
+    else:
+        # the batch is split into `--streams` sub-batches, each on its own CUDA stream and host thread
+        group = ScoreSolverGroup(prob, n_streams=args.streams, device=local_rank, n_parts=args.parts)
+        # warm-up and timed region both run the steps as a pipeline (ScoreSolverGroup.solve_steps): every sub-batch is
+        # re-solved step after step by its own host thread, the sub-batches half a solve out of phase, so that the sparse
+        # last cycles of one (a few ill-conditioned instances) run under the dense first cycles of the other.  All K steps
+        # start and finish inside the timed region.
+        group.solve(kkt_tol=KKT_TOL)
+        group.solve_steps(max(args.sets, args.warmup), n_sets=args.sets, kkt_tol=KKT_TOL)
+        barrier()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        sts = group.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL)  # returns after the last solve of the last step
+        ev1.record()
+        barrier()
+        elapsed = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    t_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
-    per_rank = [[float(t_ms.item()) / args.steps, cycles / args.steps]]
+    launches = sum(st.kernel_launches for st in sts)
+    bytes_total = float(sum(st.algorithmic_bytes for st in sts))
+    solve_ms = float(sum(st.solve_ms for st in sts))
+    ticks = sum(st.ticks for st in sts)
+    cycles = sum(st.cycles for st in sts)
+    n_solved = sum(st.n_solved for st in sts)
+    n_done = sum(st.n_instances for st in sts)
+    st = sts[-1]
+    t_ms = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+    per_rank = [[float(t_ms.item()) / args.steps, cycles / args.steps, n_done / args.steps]]
     if world > 1:
         mine = torch.tensor(per_rank[0], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = [[float(v) for v in t.tolist()] for t in allr]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        agg = torch.tensor([float(n_solved), float(launches)], device="cuda", dtype=torch.float64)
+        agg = torch.tensor([float(n_solved), float(launches), float(n_done)], device="cuda", dtype=torch.float64)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        n_solved_all, launches_all = int(agg[0].item()), int(agg[1].item())
+        n_solved_all, launches_all, n_done_all = int(agg[0].item()), int(agg[1].item()), int(agg[2].item())
     else:
-        n_solved_all, launches_all = n_solved, launches
+        n_solved_all, launches_all, n_done_all = n_solved, launches, n_done
     t_ms = float(t_ms.item())
     inst_all = args.instances if args.scaling == "strong" else args.instances * world
     total_instances = inst_all * args.steps
+    if n_done_all != total_instances:
+        raise RuntimeError(f"the ranks solved {n_done_all} instances, the job has {total_instances}")
     value = total_instances / (t_ms * 1e-3)
-    inst_stats = st.instances  # per-instance records of the last timed step (objective, rel KKT, iteration counts)
+    inst_stats = st.instances  # per-instance records of one timed sub-batch job (objective, rel KKT, iteration counts)
 
     # ---- strong scaling beside the weak curve: the SAME total of --instances split over the ranks
     strong = None
@@ -454,32 +501,44 @@ def run_gpu_arm(args, rank, local_rank, world):
         from score_b200.lowering import slice_instances
 
         n_str = max(1, args.instances // world)
-        g_str = ScoreSolverGroup(slice_instances(prob, 0, n_str), n_streams=args.streams, device=local_rank, n_parts=args.parts)
-        g_str.solve(kkt_tol=KKT_TOL)
-        g_str.solve_steps(2 * args.sets, n_sets=args.sets, kkt_tol=KKT_TOL)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g_str.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL)
-        e1.record()
-        barrier()
-        ts = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        p_str = slice_instances(prob, 0, n_str)
+        if args.dynamic:
+            n_parts_str = max(1, min(n_parts_rank, n_str))
+            shards = [None] * world
+            dist.all_gather_object(shards, p_str)
+            parts_str = [pt for sh in shards for pt in split(sh, n_parts_str)]
+            del shards
+            ts_ms, _, _ = run_dynamic(parts_str, args.steps, 2)
+            ts = torch.tensor([ts_ms], device="cuda", dtype=torch.float64)
+        else:
+            g_str = ScoreSolverGroup(p_str, n_streams=args.streams, device=local_rank, n_parts=args.parts)
+            g_str.solve(kkt_tol=KKT_TOL)
+            g_str.solve_steps(2 * args.sets, n_sets=args.sets, kkt_tol=KKT_TOL)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g_str.solve_steps(args.steps, n_sets=args.sets, kkt_tol=KKT_TOL)
+            e1.record()
+            barrier()
+            ts = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            g_str.close()
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        g_str.close()
         strong = {
             "instances_total": n_str * world,
             "instances_per_gpu": n_str,
             "value": n_str * world * args.steps / (float(ts.item()) * 1e-3),
             "unit": UNIT,
             "ms_per_step": float(ts.item()) / args.steps,
-            "how": "every rank solves the first instances_per_gpu instances of its shard (same generator, same sizes): the "
-            "--instances total of the single-GPU run split over the ranks; device-timed, max over ranks",
+            "schedule": "dynamic" if args.dynamic else "static",
+            "how": "the first instances_per_gpu instances of every rank's shard (same generator, same sizes): the --instances "
+            "total of the single-GPU run split over the ranks, K steps pipelined like the weak run; device-timed, max over ranks",
         }
 
     # ---- roofline of the dominant kernel
     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
         peak = float(json.load(f)["hbm_gbs"])
-    group.close()
+    if group is not None:
+        group.close()
     solver = ScoreSolver(prob, device=local_rank)  # the kernel profile runs the whole batch on one stream
     solver.solve(kkt_tol=KKT_TOL, stream=stream)
     # (a) whole solve, un-graphed, CUDA events between all kernels: time share of every kernel and its achieved
@@ -521,7 +580,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     cg_ms = float(sum(full_ms[i] for i in cg_ids if stf.kernel_count_full[i] > 0))
     cg_bytes = float(sum(stf.kernel_bytes[i] for i in cg_ids if stf.kernel_count_full[i] > 0 and KERNEL_NAMES[i] not in NOT_HBM))
     n_i = args.instances if args.scaling != "strong" else n_local
-    nnz_r, m_r, nz_r = float(st.nnz_reduced), float(st.rows), float(st.cols)
+    nnz_r, m_r, nz_r = float(stp.nnz_reduced), float(stp.rows), float(stp.cols)
     pdhg_bytes = 24.0 * nnz_r + 4.0 * (m_r + nz_r + 2.0 * n_i) + 8.0 * (7.0 * m_r + 6.0 * nz_r)
     roofline = {
         "bound": "hbm",
@@ -622,37 +681,72 @@ def run_gpu_arm(args, rank, local_rank, world):
     if not args.no_e2e:
         import dataclasses
 
-        pinned = {}
-        for f in dataclasses.fields(prob):
-            v = getattr(prob, f.name)
-            if isinstance(v, np.ndarray):
-                t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
-                pinned[f.name] = t
-        prob_pinned = dataclasses.replace(prob, **{k: t.numpy() for k, t in pinned.items()})
+        def pin(p):
+            rep = {}
+            for f in dataclasses.fields(p):
+                v = getattr(p, f.name)
+                if isinstance(v, np.ndarray):
+                    rep[f.name] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
+            return dataclasses.replace(p, **rep)
+
         n_e2e = max(1, args.steps)
-        outs = tuple(torch.empty(shp, dtype=torch.float64).pin_memory().numpy() for shp in solver.solution_shapes())
-        # one untimed pass: first touch of the pinned buffers / allocator pool
-        solver.close()
-        g2 = ScoreSolverGroup(prob_pinned, n_streams=args.streams, device=local_rank, create=False, n_parts=args.parts)
-        g2.prewarm()  # the library's memory / stream caches then hold a spare set of handle resources
         inflight = min(4, args.streams * args.sets)  # sub-batch solves in flight (more only adds host-side contention)
-        g2.prewarm(extra=inflight - args.streams)
-        g2.run_pipelined(out=outs, steps=2, inflight=inflight, kkt_tol=KKT_TOL)  # same queue depth as the timed run
-        barrier()
-        t0 = time.perf_counter()
-        h2d = d2h = 0
-        _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, inflight=inflight, kkt_tol=KKT_TOL)  # returns after the last read-back
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        g2.close()
-        if world > 1:
+        solver.close()
+        if args.dynamic:
+            # the same queue over all ranks, every job from HOST buffers: score_create (H2D) + solve + read-back (D2H)
+            from score_b200.sharding import JobCounter, SweepQueue
+            from score_b200.solver import StreamedJobs
+
+            parts_pinned = [pin(pt) for pt in parts_global]
+            d = prob.dim
+            mx = lambda name: max(getattr(pt, name) for pt in parts_pinned)
+            slot = lambda: (torch.empty((mx("P"), d, d + 1), dtype=torch.float64).pin_memory().numpy(),
+                            torch.empty((mx("P"), d, d), dtype=torch.float64).pin_memory().numpy(),
+                            torch.empty((mx("L"), d), dtype=torch.float64).pin_memory().numpy(),
+                            torch.empty((mx("K"), parts_pinned[0].dist_per), dtype=torch.float64).pin_memory().numpy())
+            jobs = StreamedJobs(parts_pinned, [slot() for _ in range(inflight + 1)], device=local_rank, inflight=inflight)
+            g2 = ScoreSolverGroup(parts_pinned[0], n_streams=1, device=local_rank, create=False)
+            g2.prewarm(extra=inflight)  # the library's memory / stream caches then hold enough for the queue depth
+            g2.close()
+            counter = JobCounter(dist.distributed_c10d._get_default_store(), key="score_b200/bench/e2e")
+            with SweepQueue(len(parts_pinned), lambda step, part, w: jobs(step, part, w, kkt_tol=KKT_TOL), counter,
+                            inflight=inflight + 1) as q:
+                q.run(2, costs_global)
+                jobs.h2d_bytes = jobs.d2h_bytes = 0
+                barrier()
+                t0 = time.perf_counter()
+                q.run(n_e2e, costs_global)  # returns after this rank's last read-back
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            moved = torch.tensor([float(jobs.h2d_bytes), float(jobs.d2h_bytes)], device="cuda", dtype=torch.float64)
             dist.barrier()
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(moved, op=dist.ReduceOp.SUM)
+            h2d_step, d2h_step = int(moved[0].item()) // n_e2e, int(moved[1].item()) // n_e2e
+        else:
+            prob_pinned = pin(prob)
+            outs = tuple(torch.empty(shp, dtype=torch.float64).pin_memory().numpy() for shp in solver.solution_shapes())
+            # one untimed pass: first touch of the pinned buffers / allocator pool
+            g2 = ScoreSolverGroup(prob_pinned, n_streams=args.streams, device=local_rank, create=False, n_parts=args.parts)
+            g2.prewarm()  # the library's memory / stream caches then hold a spare set of handle resources
+            g2.prewarm(extra=inflight - args.streams)
+            g2.run_pipelined(out=outs, steps=2, inflight=inflight, kkt_tol=KKT_TOL)  # same queue depth as the timed run
+            barrier()
+            t0 = time.perf_counter()
+            _, _, h2d, d2h = g2.run_pipelined(out=outs, steps=n_e2e, inflight=inflight, kkt_tol=KKT_TOL)  # returns after the last read-back
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            g2.close()
+            if world > 1:
+                dist.barrier()
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            h2d_step, d2h_step = int(h2d) * world, int(d2h) * world
         e2e = {
             "value": inst_all * n_e2e / float(dt.item()),
             "unit": UNIT,
-            "h2d_bytes_per_step": int(h2d) * world,
-            "d2h_bytes_per_step": int(d2h) * world,
+            "h2d_bytes_per_step": h2d_step,
+            "d2h_bytes_per_step": d2h_step,
+            "schedule": "dynamic" if args.dynamic else "static",
             "steps": n_e2e,
             "streams": args.streams,
             "parts": args.parts or args.streams,

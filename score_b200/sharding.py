@@ -119,6 +119,100 @@ def solve_score_sharded(datas, relaxation_type: str = "QCQP", device: Optional[i
     return gather_results(mine, local, len(datas), group=group, dst=dst)
 
 
+class JobCounter:
+    """Fetch-and-add counter shared by all ranks: the c10d key-value store's atomic ``add`` (TCPStore / the default
+    store of the process group), or a lock-protected integer inside one process (``store=None``)."""
+
+    def __init__(self, store=None, key: str = "score_b200/sweep_queue"):
+        import threading
+
+        self.store, self.key = store, key
+        self._lock, self._local = threading.Lock(), {}
+
+    def next(self, epoch: int) -> int:
+        """The next unclaimed job number of run ``epoch`` (0, 1, 2, ... across all ranks and threads)."""
+        if self.store is not None:
+            return int(self.store.add(f"{self.key}/{epoch}", 1)) - 1
+        with self._lock:
+            v = self._local.get(epoch, 0)
+            self._local[epoch] = v + 1
+            return v
+
+
+class SweepQueue:
+    """Dynamic schedule of a Monte-Carlo sweep over the ranks ("the only loss is tail imbalance
+    from per-instance iteration counts => dynamic chunking").
+
+    The sweep is cut into ``n_parts`` sub-batches that every rank can solve (the lowered inputs are small: ~0.2 MB per
+    instance, so each rank keeps all of them; on the device-resident path as ready handles).  ``steps`` passes over the
+    sweep are ONE queue of ``steps x n_parts`` jobs; ``inflight`` host threads per rank claim the next job from a
+    counter shared by all ranks (``JobCounter``) and run it on their GPU, so that a rank that drew an ill-conditioned
+    sub-batch (its slowest instance needs 2-3x the cycles of a typical one) simply claims fewer jobs instead of holding
+    every step back.  Inside a pass the sub-batches are handed out longest first (``costs``, e.g. the solve times of a
+    warm-up pass), which keeps the last jobs of the queue short.  There is still no data-path collective: the counter is
+    a host-side store operation per job (16 per 8192-instance pass).
+
+    ``job_fn(step, part, worker) -> result`` runs one job (bench.py / ``solve_parts``: a ``score_solve`` on a pooled
+    handle, or create -> solve -> read back -> destroy from host buffers).  Results are bit-identical to a static
+    schedule: an instance's arithmetic does not depend on where or next to what it is solved.
+    """
+
+    def __init__(self, n_parts: int, job_fn: Callable, counter: Optional[JobCounter] = None, inflight: int = 4):
+        if n_parts < 1 or inflight < 1:
+            raise ValueError("n_parts and inflight must be >= 1")
+        self.n_parts, self.job_fn, self.inflight = int(n_parts), job_fn, int(inflight)
+        self.counter = counter if counter is not None else JobCounter()
+        self.epoch = 0
+        self._pool = None
+
+    def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def job_order(costs: Optional[Sequence[float]], n_parts: int) -> List[int]:
+        """Sub-batch order inside a pass: descending cost, ties by index (the same on every rank)."""
+        if costs is None:
+            return list(range(n_parts))
+        if len(costs) != n_parts:
+            raise ValueError("one cost per sub-batch")
+        return sorted(range(n_parts), key=lambda i: (-float(costs[i]), i))
+
+    def run(self, steps: int, costs: Optional[Sequence[float]] = None) -> List[tuple]:
+        """Work through this run's queue together with the other ranks (every rank must call ``run`` the same number
+        of times with the same ``steps`` / ``costs``).  Returns the jobs THIS rank ran as (step, part, result), in
+        completion order; returns when the queue is empty and this rank's last job has finished."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        order = self.job_order(costs, self.n_parts)
+        total = int(steps) * self.n_parts
+        epoch = self.epoch
+        self.epoch += 1
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(self.inflight)
+
+        def worker(w):
+            done = []
+            while True:
+                j = self.counter.next(epoch)
+                if j >= total:
+                    return done
+                step, part = j // self.n_parts, order[j % self.n_parts]
+                done.append((step, part, self.job_fn(step, part, w)))
+
+        out: List[tuple] = []
+        for d in self._pool.map(worker, range(self.inflight)):
+            out.extend(d)
+        return out
+
+
 def row_block_range(n_blocks: int, rank: int, world_size: int) -> range:
     """Row blocks (of 768 measurement rows) rank ``rank`` owns in a row-partitioned solve — the same split
     ``score_comm_init`` computes on the device side (api.cu)."""

@@ -446,6 +446,88 @@ class ScoreSolverGroup:
                 sum(r[2] for r in res) // steps)
 
 
+class HandlePool:
+    """Ready handles for a list of sub-batches, ``copies`` per sub-batch (device-resident inputs): the job function of
+    a dynamically scheduled sweep (``sharding.SweepQueue``) borrows one for the duration of a ``score_solve``.  Two
+    copies let two passes over the same sub-batch be in flight on one GPU; a third borrower waits."""
+
+    def __init__(self, parts: List[LoweredProblem], device: int = 0, copies: int = 2, threads: int = 4):
+        import queue
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.parts, self.device = list(parts), device
+        self._free = [queue.Queue() for _ in self.parts]
+        self._all: List[ScoreSolver] = []
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            made = list(ex.map(lambda g: ScoreSolver(self.parts[g], device=device),
+                               [g for g in range(len(self.parts)) for _ in range(max(1, copies))]))
+        for k, h in enumerate(made):
+            self._all.append(h)
+            self._free[k // max(1, copies)].put(h)
+
+    def solve(self, part: int, **kw) -> SolveStats:
+        kw.pop("stream", None)  # every handle runs on its own library-owned stream
+        h = self._free[part].get()
+        try:
+            return h.solve(**kw)
+        finally:
+            self._free[part].put(h)
+
+    def warm(self, threads: int = 4, **kw) -> List[SolveStats]:
+        """Solve on EVERY handle once (first-use work: graph capture, workspace) — one SolveStats per sub-batch (of its
+        last copy; iteration counts are deterministic, so every rank sees the same)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        kw.pop("stream", None)
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            sts = list(ex.map(lambda h: h.solve(**kw), self._all))
+        copies = len(self._all) // max(1, len(self.parts))
+        return [sts[g * copies + copies - 1] for g in range(len(self.parts))]
+
+    def close(self) -> None:
+        for h in self._all:
+            h.close()
+        self._all = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class StreamedJobs:
+    """create -> solve -> read-back -> destroy of one sub-batch per call, from HOST arrays (the end-to-end job of a
+    dynamically scheduled sweep): at most ``inflight`` solves at a time on this GPU while one more thread may already be
+    inside ``score_create`` of the next job; results land in the calling worker's own (pinned) output slot."""
+
+    def __init__(self, parts: List[LoweredProblem], outs: List[tuple], device: int = 0, inflight: int = 4):
+        import threading
+
+        self.parts, self.outs, self.device = list(parts), outs, device
+        self._solving = threading.Semaphore(max(1, inflight))
+        self._creating = threading.Lock()
+        self.h2d_bytes = self.d2h_bytes = 0
+        self._acc = threading.Lock()
+
+    def views(self, worker: int, prob: LoweredProblem):
+        o = self.outs[worker]
+        return (o[0][: prob.P], o[1][: prob.P], o[2][: prob.L], o[3][: prob.K])
+
+    def __call__(self, step: int, part: int, worker: int, **kw) -> SolveStats:
+        prob = self.parts[part]
+        with self._creating:
+            s = ScoreSolver(prob, device=self.device)
+        with s:
+            with self._solving:
+                st = s.solve(**kw)
+            s.solution(out=self.views(worker, prob))
+            with self._acc:
+                self.h2d_bytes += s.h2d_bytes
+                self.d2h_bytes += s.d2h_bytes
+        return st
+
+
 def round_to_special_orthogonal_batch(mats: np.ndarray, device: int = 0) -> np.ndarray:
     """SO(d) rounding of a stack of d x d matrices on the GPU (score_round_so)."""
     mats = _f64(mats)

@@ -601,3 +601,53 @@ def test_pipelined_steps_match_plain_solve_bitwise(built_lib):
         assert np.array_equal(k.instances["objective"], st.instances["objective"])
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
+
+
+def test_dynamic_sweep_queue_matches_plain_solve_bitwise(built_lib):
+    """sharding.SweepQueue over pooled handles (device-resident) and over create -> solve -> read-back jobs (host buffers):
+    every job's per-instance records and read-back arrays equal a plain single-handle solve of the same instances."""
+    from score_b200 import generators
+    from score_b200.lowering import concat, lower_manhattan_arrays, slice_instances
+    from score_b200.sharding import SweepQueue
+    from score_b200.solver import HandlePool, ScoreSolver, StreamedJobs
+
+    batch = concat([lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=3 + i % 2,
+                                                                           n_steps=24 + 2 * i)) for i in range(7)])
+    cuts = [0, 2, 5, 7]
+    parts = [slice_instances(batch, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    with ScoreSolver(batch) as s:
+        st = s.solve()
+        ref = s.solution()
+    assert st.n_solved == 7
+    with HandlePool(parts, copies=2) as pool:
+        costs = [float(w.cycles) for w in pool.warm()]
+        with SweepQueue(len(parts), lambda step, part, w: pool.solve(part), inflight=4) as q:
+            res = q.run(4, costs)
+    assert sorted((s_, p) for s_, p, _ in res) == [(s_, p) for s_ in range(4) for p in range(3)]
+    for _, p, r in res:
+        a, b = cuts[p], cuts[p + 1]
+        assert r.n_solved == b - a
+        assert np.array_equal(r.instances["cg_iters"], st.instances["cg_iters"][a:b])
+        assert np.array_equal(r.instances["objective"], st.instances["objective"][a:b])
+    # host-buffer jobs: every worker reads back into its own slot; the slot of the last job of a worker holds that part
+    d = batch.dim
+    big = lambda: (np.empty((batch.P, d, d + 1)), np.empty((batch.P, d, d)), np.empty((batch.L, d)),
+                   np.empty((batch.K, batch.dist_per)))
+    outs = [big() for _ in range(3)]
+    jobs = StreamedJobs(parts, outs, inflight=2)
+    last = {}
+
+    def job(step, part, w):
+        r = jobs(step, part, w)
+        last[w] = (part, [v.copy() for v in jobs.views(w, parts[part])])
+        return r
+
+    with SweepQueue(len(parts), job, inflight=3) as q:
+        res = q.run(2, costs)
+    assert len(res) == 6 and jobs.h2d_bytes > 0 and jobs.d2h_bytes > 0
+    for w, (p, arrs) in last.items():
+        a, b = cuts[p], cuts[p + 1]
+        assert np.array_equal(arrs[0], ref[0][batch.pose_off[a]:batch.pose_off[b]])
+        assert np.array_equal(arrs[1], ref[1][batch.pose_off[a]:batch.pose_off[b]])
+        assert np.array_equal(arrs[2], ref[2][batch.lm_off[a]:batch.lm_off[b]])
+        assert np.array_equal(arrs[3], ref[3][batch.rng_off[a]:batch.rng_off[b]])

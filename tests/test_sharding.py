@@ -111,3 +111,85 @@ def test_gather_detects_double_assignment():
         gather_results([0, 0], ["a", "b"], 2)
     with pytest.raises(RuntimeError):
         gather_results([0], ["a"], 2)
+
+
+def test_sweep_queue_single_process_order_and_coverage():
+    """One process: every (step, part) job runs exactly once, longest sub-batch first inside a step."""
+    import threading
+
+    from score_b200.sharding import SweepQueue
+
+    claimed, lock = [], threading.Lock()
+
+    def job(step, part, worker):
+        with lock:
+            claimed.append((step, part))
+        return part * 10 + step
+
+    costs = [3.0, 9.0, 1.0, 9.0]
+    assert SweepQueue.job_order(costs, 4) == [1, 3, 0, 2]
+    assert SweepQueue.job_order(None, 3) == [0, 1, 2]
+    with SweepQueue(4, job, inflight=1) as q:  # one worker: the claim order is the queue order
+        res = q.run(3, costs)
+        assert claimed == [(s, p) for s in range(3) for p in (1, 3, 0, 2)]
+        assert [(s, p) for s, p, _ in res] == claimed and all(r == p * 10 + s for s, p, r in res)
+        claimed.clear()
+        res = q.run(2)  # a second run starts a fresh counter
+        assert sorted(claimed) == [(s, p) for s in range(2) for p in range(4)]
+    with SweepQueue(5, job, inflight=3) as q:
+        claimed.clear()
+        res = q.run(4, [1, 2, 3, 4, 5])
+        assert sorted((s, p) for s, p, _ in res) == [(s, p) for s in range(4) for p in range(5)]
+    with pytest.raises(ValueError):
+        SweepQueue(0, job)
+    with pytest.raises(ValueError):
+        SweepQueue.job_order([1.0], 2)
+
+
+def _queue_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import time
+
+    import torch.distributed as dist
+
+    from score_b200.sharding import JobCounter, SweepQueue
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        store = dist.distributed_c10d._get_default_store()
+
+        def job(step, part, worker):  # rank 1 is the slow GPU: every job takes 4x longer there
+            time.sleep(0.02 if rank == 0 else 0.08)
+            return (rank, step, part)
+
+        runs = []
+        with SweepQueue(6, job, JobCounter(store, key="test/q"), inflight=2) as q:
+            for _ in range(2):
+                dist.barrier()
+                runs.append(q.run(5, [1, 6, 2, 5, 3, 4]))
+        out.put((rank, runs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sweep_queue_gloo_world2():
+    """Two ranks drain one queue through the process group's store: every job exactly once per run, the slow rank
+    claims fewer."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_queue_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for run in range(2):
+        jobs = [(s, p) for r in (0, 1) for s, p, _ in got[r][run]]
+        assert sorted(jobs) == [(s, p) for s in range(5) for p in range(6)]  # each job exactly once, none lost
+        assert all(res == (r, s, p) for r in (0, 1) for s, p, res in got[r][run])
+        n0, n1 = len(got[0][run]), len(got[1][run])
+        assert n0 > n1 >= 1  # the fast rank took more of the queue
