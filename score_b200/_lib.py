@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscore_b200.so")
+# SCORE_B200_LIB: an alternative build of the same library (A/B runs of compile-time variants, scripts/runs/)
+LIB_PATH = os.environ.get("SCORE_B200_LIB") or os.path.join(_HERE, "libscore_b200.so")
 
 SCORE_RELAX_QCQP, SCORE_RELAX_SOCP = 0, 1
 SCORE_CSR_FULL, SCORE_CSR_REDUCED, SCORE_CSR_REDUCED_T = 0, 1, 2

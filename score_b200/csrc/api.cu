@@ -24,6 +24,10 @@
 #include "precond.cuh"
 #include "solver.cuh"
 
+#ifndef SCORE_EVENT_SYNC_FLAG
+#define SCORE_EVENT_SYNC_FLAG cudaEventBlockingSync
+#endif
+
 thread_local std::string g_score_last_error;
 
 // NCCL is bound at run time, and only when a row-partitioned solve asks for it: the library then shares the
@@ -281,7 +285,9 @@ struct ResourceCache {
         return cudaSuccess;
       }
     }
-    return cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    // blocking sync: a host thread waiting for a cycle to finish sleeps instead of spinning on a core (a sweep keeps
+    // several solves in flight per GPU, 8 ranks per host: spinning waiters starve the threads that upload and launch)
+    return cudaEventCreateWithFlags(ev, cudaEventDisableTiming | SCORE_EVENT_SYNC_FLAG);
   }
   void put_event(int dev, cudaEvent_t ev) {
     std::lock_guard<std::mutex> lk(mu);

@@ -629,8 +629,11 @@ __global__ void __launch_bounds__(kThreads) k_grad_mf(DevProblem P, SolverVecs V
   }
 }
 
+#ifndef SCORE_HV_MINB
+#define SCORE_HV_MINB 4
+#endif
 template <int D>
-__global__ void __launch_bounds__(kThreads, 4) k_hessvec(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kThreads, SCORE_HV_MINB) k_hessvec(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);

@@ -11,6 +11,18 @@
 #pragma once
 #include "common.cuh"
 
+// CTAs of kSegThreads threads per SM the chain-scan kernels are compiled for.  d = 2: 16 = every thread slot of the SM
+// (32 registers per thread, a few spilled words).  These kernels are bound by the latency of their dependent rounds of
+// loads, and 16 resident segments per SM measured 614 us per PCG tick of the 1024-instance sweep against 649 us with
+// the compiler's own choice (40 / 56 registers, 12 / 9 CTAs per SM) — profiles/occupancy_r2.txt.  d = 3 (12-entry
+// pose blocks): 8 CTAs, 64 registers.
+#ifndef SCORE_PC_MINB
+#define SCORE_PC_MINB 16
+#endif
+#ifndef SCORE_PC_MINB3
+#define SCORE_PC_MINB3 8
+#endif
+
 namespace score {
 
 // One thread per segment: G_p = [Rg|tg], sequential composition (setup only).
@@ -346,7 +358,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
 
 // Listed instance x (its chain segments, then its landmark block: slot W.maxseg).
 template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_precond_rev(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kSegThreads, D == 2 ? SCORE_PC_MINB : SCORE_PC_MINB3) k_precond_rev(DevProblem P, SolverVecs V, const InstState *st, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
@@ -458,7 +470,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
 }
 
 template <int D>
-__global__ void __launch_bounds__(kSegThreads) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st, WorkLists W,
+__global__ void __launch_bounds__(kSegThreads, D == 2 ? SCORE_PC_MINB : SCORE_PC_MINB3) k_precond_fwd(DevProblem P, SolverVecs V, const InstState *st, WorkLists W,
                                                             const bool fuse) {
   const int *act;
   int n_act;

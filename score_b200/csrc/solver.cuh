@@ -23,6 +23,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SCORE_LS_MINB
+#define SCORE_LS_MINB 3
+#endif
+#ifndef SCORE_RU_MINB
+#define SCORE_RU_MINB 4
+#endif
+
 namespace score {
 
 __device__ __forceinline__ double ls_candidate(int c) {
@@ -335,7 +342,7 @@ __device__ __forceinline__ void linesearch_body(DevProblem P, SolverVecs V, Bloc
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 3) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
+__global__ void __launch_bounds__(kThreads, SCORE_LS_MINB) k_linesearch(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, WorkLists W) {
   const int *act;
   int n_act;
   wl_get(W, WL_LS, act, n_act);
@@ -531,7 +538,7 @@ __device__ __forceinline__ void rowupdate_body(DevProblem P, SolverVecs V, Block
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
+__global__ void __launch_bounds__(kThreads, SCORE_RU_MINB) k_rowupdate(DevProblem P, SolverVecs V, BlockTables T, const InstState *st,
                                                         int mode, WorkLists W) {
   const int *act;
   int n_act;
