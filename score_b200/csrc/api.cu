@@ -90,6 +90,7 @@ struct ScoreHandle_ {
   // host copies of the offset tables
   std::vector<int> pose_off, lm_off, edge_off, rng_off, prior_off, zoff, roff, nnzoff, seg_begin;
   std::vector<int> rb_begin, cb_begin, pb_begin;
+  int n_pbd = 0;  // entries of the dense Hessian-vector item table
   void *inc_tmp = nullptr;  // radix-sort scratch of the incidence lists
   uint4 *inc_in = nullptr;  // unsorted incidence records
   size_t inc_tmp_bytes = 0;
@@ -1036,6 +1037,15 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   UP(roff, h->roff.data(), NI + 1)
   UP(nnzoff, h->nnzoff.data(), NI + 1)
   UP(seg_begin, h->seg_begin.data(), NI + 1)
+  {  // dense item table of the chain-scan kernels: segment j of instance i at [i * maxseg + j]
+    int maxseg = 1;
+    for (int i = 0; i < NI; ++i) maxseg = std::max(maxseg, h->seg_begin[i + 1] - h->seg_begin[i]);
+    std::vector<int4> tab((size_t)NI * maxseg, make_int4(-1, -1, -1, 0));
+    for (int i = 0; i < NI; ++i)
+      for (int sg = h->seg_begin[i]; sg < h->seg_begin[i + 1]; ++sg)
+        tab[(size_t)i * maxseg + (sg - h->seg_begin[i])] = make_int4(seg_ptr[sg], seg_ptr[sg + 1], sg, 0);
+    UP(seg_tab, tab.data(), tab.size())
+  }
   UP(seg_ptr, seg_ptr.data(), P.n_seg + 1)
   UP(seg_inst, seg_inst.data(), P.n_seg)
   UP(link_edge, desc->link_edge, P.P)
@@ -1173,13 +1183,24 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
     const int Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
     const int z0 = h->zoff[i], pg0 = h->pose_off[i], lg0 = h->lm_off[i];
     for (int p0 = 0; p0 < Pi; p0 += kPosesPerBlock)
-      pb.push_back({i, p0, std::min(p0 + kPosesPerBlock, Pi), CB_POSE, z0, pg0, Pi, lg0});
+      pb.push_back({i, p0, std::min(p0 + kPosesPerBlock, Pi), CB_POSE, z0, pg0, Pi, lg0, (int)pb.size(), 0, 0, 0});
     for (int q0 = 0; q0 < Li; q0 += kLmPerBlock)
-      pb.push_back({i, q0, std::min(q0 + kLmPerBlock, Li), CB_LANDMARK, z0, pg0, Pi, lg0});
+      pb.push_back({i, q0, std::min(q0 + kLmPerBlock, Li), CB_LANDMARK, z0, pg0, Pi, lg0, (int)pb.size(), 0, 0, 0});
   }
   h->pb_begin[NI] = (int)pb.size();
   h->T.n_pb = (int)pb.size();
   if ((rc = upload(h, &h->T.pb, pb.data(), pb.size()))) return rc;
+  {  // dense item table: block j of instance i at [i * maxpb + j] (jb / je are filled on the device: k_hv_fill)
+    int maxpb = 1;
+    for (int i = 0; i < NI; ++i) maxpb = std::max(maxpb, h->pb_begin[i + 1] - h->pb_begin[i]);
+    HvBlock none{};
+    none.kind = -1;
+    std::vector<HvBlock> dense((size_t)NI * maxpb, none);
+    for (int i = 0; i < NI; ++i)
+      for (int b = h->pb_begin[i]; b < h->pb_begin[i + 1]; ++b) dense[(size_t)i * maxpb + (b - h->pb_begin[i])] = pb[b];
+    h->n_pbd = (int)dense.size();
+    if ((rc = upload(h, &h->T.pbd, dense.data(), dense.size()))) return rc;
+  }
   if ((rc = upload(h, &h->T.pb_begin, h->pb_begin.data(), NI + 1))) return rc;
   h->T.n_rb = (int)rb.size();
   h->T.n_cb = (int)cb.size();
@@ -1820,7 +1841,8 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
       SCORE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->inc_tmp, h->inc_tmp_bytes, h->sort_idx, h->sort_keys, h->inc_in,
                                                        P.inc_rec, P.n_inc, 0, ob, st));
       k_inc_ptr<<<grid_for(P.n_inc, 256), 256, 0, st>>>(P.n_inc, P.P + P.L, h->sort_keys, P.inc_ptr);
-      launches += 4;
+      k_hv_fill<<<grid_for(h->T.n_pb + h->n_pbd, 256), 256, 0, st>>>(P, h->T, h->n_pbd);
+      launches += 5;
     } else {
       SCORE_CUDA_CHECK(cudaMemsetAsync(P.inc_ptr, 0, sizeof(int) * ((size_t)P.P + P.L + 1), st));
     }

@@ -59,6 +59,8 @@ struct DevProblem {
   int *zoff, *roff, *nnzoff;
   int *seg_ptr, *seg_inst, *link_edge;
   int *seg_begin;  // [n_inst+1] first segment of each instance
+  int4 *seg_tab;   // [n_inst x maxseg] {first pose, end pose, segment, 0} of segment j of an instance (first pose -1: none):
+                   // what a chain-scan CTA needs about its work item in one 16-byte load (WorkLists.maxseg is the stride)
   // factors
   int *edge_i, *edge_j;
   double *edge_t, *edge_R, *edge_k, *edge_tau;
@@ -127,13 +129,15 @@ constexpr int kTraceRec = 8;
 // Work descriptor of one CTA of the matrix-free Hessian-vector kernel: poses / landmarks [i0, i1) of instance `inst`
 // (instance-local), plus what the kernel would otherwise fetch through two more dependent loads.
 struct HvBlock {
-  int inst, i0, i1, kind;
-  int z0, pg0, Pi, lg0;  // column base, global index of the instance's first pose, its pose count, first global landmark
+  int inst, i0, i1, kind;  // kind < 0: no such block (padding of the dense item table)
+  int z0, pg0, Pi, lg0;    // column base, global index of the instance's first pose, its pose count, first global landmark
+  int bid, jb, je, pad;    // index in the compact table (partial sums); pose blocks: the block's run of incidence records
 };
 
 struct BlockTables {
   BlockDesc *rb, *cb;  // row blocks, column blocks
   HvBlock *pb;         // pose / landmark blocks of the Hessian-vector kernel
+  HvBlock *pbd;        // the same as a dense item table [n_inst x WorkLists.maxpb]: one 48-byte load per work item
   int n_rb, n_cb, n_pb;
   int *rb_begin, *cb_begin, *pb_begin;  // [n_inst+1]
 };

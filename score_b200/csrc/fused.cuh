@@ -95,13 +95,16 @@ __global__ void __launch_bounds__(kThreads) k_pcg_fused(DevProblem P, SolverVecs
       // ---- s = P r: reverse scans (+ coarse right-hand side), then coarse solve + forward scans
       if (threadIdx.x < kSegThreads)
         for (int j = crank; j <= nseg; j += NB) {
-          precond_rev_body<D, true>(P, V, st, j < nseg ? sg0 + j : P.n_seg + inst);
+          if (j < nseg)
+            precond_rev_body<D, true>(P, V, st, sg0 + j, inst, P.seg_ptr[sg0 + j], P.seg_ptr[sg0 + j + 1]);
+          else
+            precond_rev_body<D, true>(P, V, st, P.n_seg + inst, inst, 0, 0);
           seg_bar<true>();
         }
       sync_all();
       if (threadIdx.x < kSegThreads)
         for (int j = crank; j < nseg; j += NB) {
-          precond_fwd_body<D, true>(P, V, st, sg0 + j, true);
+          precond_fwd_body<D, true>(P, V, st, sg0 + j, inst, P.seg_ptr[sg0 + j], P.seg_ptr[sg0 + j + 1], true);
           seg_bar<true>();
         }
       sync_all();

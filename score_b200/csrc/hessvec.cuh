@@ -227,15 +227,17 @@ __device__ __forceinline__ double range_contrib(const double *xz, const double *
   return dc;
 }
 
+// The descriptor carries everything the CTA needs to address its loads, so the instance state, the links, the list
+// bounds, the own x block and the first incidence record of every thread go out in ONE round (all addresses are valid
+// whatever the state says); the state is looked at after they have been issued.
 template <int D>
-__device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTables T, const InstState *st, const int bid) {
+__device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, const InstState *st, const HvBlock bd) {
   constexpr int D1 = D + 1, BLK = D * D1;
   __shared__ double red[16 * (kThreads / 32)];
   __shared__ double qsh;
   __shared__ double contrib[kHvTile * D];
-  const HvBlock bd = T.pb[bid];
-  const int inst = bd.inst;
-  if (st[inst].phase != PH_CG || st[inst].eval_now) return;
+  const int inst = bd.inst, bid = bd.bid;
+  const int phase = st[inst].phase, evn = st[inst].eval_now;
   const int z0 = bd.z0, Pi = bd.Pi;
   const double *xz = V.p + z0;  // this instance's block of the direction vector
   const IncRec *__restrict__ recs = reinterpret_cast<const IncRec *>(P.inc_rec);
@@ -245,17 +247,23 @@ __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTa
     const int np = bd.i1 - bd.i0, pgf = bd.pg0 + bd.i0;  // poses of this block, global index of the first one
     const int p = bd.i0 + tid;                           // instance-local pose of this thread
     const bool active = tid < np;
-    const int jb = P.inc_ptr[pgf], je = P.inc_ptr[pgf + np];
-    int j0 = 0, j1 = 0;
+    const int jb = bd.jb, je = bd.je;
+    int j0 = 0, j1 = 0, e_in = -1, e_out = -1;
     double h[BLK], xo[BLK];
+    IncRec pre = make_uint4(0u, 0u, 0u, 0u);  // this thread's first record of the block's run
+    if (jb + tid < je) pre = recs[jb + tid];
 #pragma unroll
     for (int i = 0; i < BLK; ++i) h[i] = 0.0;
     if (active) {
       // odometry links straight from link_edge: the neighbours' blocks are at p - 1 / p + 1
-      const int e_in = P.link_edge[pgf + tid], e_out = (p + 1 < Pi) ? P.link_edge[pgf + tid + 1] : -1;
+      e_in = P.link_edge[pgf + tid];
+      e_out = (p + 1 < Pi) ? P.link_edge[pgf + tid + 1] : -1;
       j0 = P.inc_ptr[pgf + tid];
       j1 = P.inc_ptr[pgf + tid + 1];
       load_pose<D>(xz, 0, p, xo);
+    }
+    if (phase != PH_CG || evn) return;
+    if (active) {
       if (e_in >= 0) {  // (p-1 -> p): this pose is the `to` pose
         double xn[BLK], tm[D], Rm[D * D], k2, tau2;
         load_pose<D>(xz, 0, p - 1, xn);
@@ -276,7 +284,7 @@ __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTa
       const int t1 = min(je, t0 + kHvTile);
 #pragma unroll 2
       for (int j = t0 + tid; j < t1; j += kThreads) {
-        const IncRec rec = recs[j];
+        const IncRec rec = (j == jb + tid) ? pre : recs[j];
         const int kind = (int)(rec.x >> kIncShift);
         if (kind == INC_RA || kind == INC_RB) {
           double c[D];
@@ -325,6 +333,7 @@ __device__ __forceinline__ void hessvec_body(DevProblem P, SolverVecs V, BlockTa
     return;
   }
   // landmark block: landmarks bd.i0 .. bd.i1 (instance-local), each reduced by the whole CTA in fixed order
+  if (phase != PH_CG || evn) return;
   double qtot = 0.0;  // thread 0 only
   for (int q = bd.i0; q < bd.i1; ++q) {
     double v[16];
@@ -638,10 +647,21 @@ __global__ void __launch_bounds__(kThreads, SCORE_HV_MINB) k_hessvec(DevProblem 
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxpb; item += gridDim.x) {
-    const int inst = act[item / W.maxpb], bid = T.pb_begin[inst] + (int)(item % W.maxpb);
-    if (bid < T.pb_begin[inst + 1]) hessvec_body<D>(P, V, T, st, bid);
+    const int inst = act[item / W.maxpb];
+    const HvBlock bd = T.pbd[(size_t)inst * W.maxpb + (int)(item % W.maxpb)];
+    if (bd.kind >= 0) hessvec_body<D>(P, V, st, bd);
     __syncthreads();
   }
+}
+
+// jb / je of every pose block (compact and dense tables) once the incidence lists exist
+__global__ void k_hv_fill(DevProblem P, BlockTables T, int n_dense) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_pb + n_dense) return;
+  HvBlock *b = i < T.n_pb ? T.pb + i : T.pbd + (i - T.n_pb);
+  if (b->kind != CB_POSE) return;
+  b->jb = P.inc_ptr[b->pg0 + b->i0];
+  b->je = P.inc_ptr[b->pg0 + b->i1];
 }
 
 }  // namespace score

@@ -264,21 +264,28 @@ __device__ __forceinline__ void cta_scan(double (&v)[NV], double (*wtot)[NV], do
 // ---- s = P r, pass 1 (reverse): S_p = sum_{q>=p} r_q G_q^T ;  Y_p = S_p M_p -> ytmp.
 // With the coarse level on, the base block S_first goes to the coarse right-hand side instead.
 // CTA per chain segment; CTAs past n_seg handle the landmark block of one instance each.
+// `s` = segment (s < n_seg; [p0, p1) its global pose range) or n_seg + inst (the landmark block of instance `inst`).
+// The caller passes what it already knows (inst; the segment's bounds from the dense item table) so that the body's
+// own loads — instance state, offsets — go out in ONE round before the data loads instead of four dependent ones.
 template <int D, bool SUB = false>
-__device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, const InstState *st, int s) {
+__device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, const InstState *st, const int s, const int inst,
+                                                 const int p0, const int p1) {
   constexpr int D1 = D + 1, NV = D * D1;
   __shared__ double wtot[kSegThreads / 32][NV];
   __shared__ double carry[NV];
   __shared__ double red[kSegThreads / 32];
   const int tid = threadIdx.x;
+  // one round: every address below is valid whatever the state says
+  const int phase = st[inst].phase, evn = st[inst].eval_now;
+  const int zo = P.zoff[inst], po = P.pose_off[inst], cn = P.c_n[inst], coff = P.c_off[inst];
   if (s >= P.n_seg) {
-    const int inst = s - P.n_seg;
-    if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
-    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst];
-    const int n = (P.lm_off[inst + 1] - P.lm_off[inst]) * D;
-    const int c0 = P.zoff[inst] + Pi * P.blk, j0 = P.lm_off[inst] * D;
-    if (P.c_n[inst] > 0) {
-      double *c = P.c_rhs + P.c_off[inst] + P.c_nb[inst];
+    const int po1 = P.pose_off[inst + 1], l0 = P.lm_off[inst], l1 = P.lm_off[inst + 1], cnb = P.c_nb[inst];
+    if (phase == PH_DONE || phase == PH_WAIT || evn) return;
+    const int Pi = po1 - po;
+    const int n = (l1 - l0) * D;
+    const int c0 = zo + Pi * P.blk, j0 = l0 * D;
+    if (cn > 0) {
+      double *c = P.c_rhs + coff + cnb;
       for (int j = tid; j < n; j += kSegThreads) c[j] = V.r[c0 + j];
       return;
     }
@@ -293,12 +300,12 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
     if (tid == 0) V.part_lm[inst] = tot;
     return;
   }
-  const int inst = P.seg_inst[s];
-  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
-  const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
-  const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
-  const int slot = s - P.seg_begin[inst] - 1;  // -1: pinned segment
-  const bool to_coarse = P.c_n[inst] > 0 && slot >= 0;
+  const int sb = P.seg_begin[inst];
+  if (phase == PH_DONE || phase == PH_WAIT || evn) return;
+  const int len = p1 - p0;
+  const long colbase = (long)zo - (long)po * NV;
+  const int slot = s - sb - 1;  // -1: pinned segment
+  const bool to_coarse = cn > 0 && slot >= 0;
 
   if (tid < NV) carry[tid] = 0.0;
   seg_bar<SUB>();
@@ -333,7 +340,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
     cta_scan<NV, SUB>(v, wtot, carry);
     if (valid) {
       if (pg == p0 && to_coarse) {
-        double *c = P.c_rhs + P.c_off[inst] + slot * NV;
+        double *c = P.c_rhs + coff + slot * NV;
 #pragma unroll
         for (int i = 0; i < NV; ++i) c[i] = v[i];
       } else {
@@ -366,9 +373,10 @@ __global__ void __launch_bounds__(kSegThreads, D == 2 ? SCORE_PC_MINB : SCORE_PC
   for (long long item = blockIdx.x; item < (long long)n_act * per; item += gridDim.x) {
     const int inst = act[item / per], j = (int)(item % per);
     if (j == W.maxseg) {
-      precond_rev_body<D>(P, V, st, P.n_seg + inst);
-    } else if (P.seg_begin[inst] + j < P.seg_begin[inst + 1]) {
-      precond_rev_body<D>(P, V, st, P.seg_begin[inst] + j);
+      precond_rev_body<D>(P, V, st, P.n_seg + inst, inst, 0, 0);
+    } else {
+      const int4 sd = P.seg_tab[(size_t)inst * W.maxseg + j];  // {first pose, end pose, segment} or first pose < 0
+      if (sd.x >= 0) precond_rev_body<D>(P, V, st, sd.z, inst, sd.x, sd.y);
     }
     __syncthreads();  // the scan's shared carry is reused by the next item
   }
@@ -380,8 +388,8 @@ __global__ void __launch_bounds__(kSegThreads, D == 2 ? SCORE_PC_MINB : SCORE_PC
 // first segment takes the landmark rows (-> s, partial r.s).  Every row is one warp's lane-strided dot product,
 // the same summation order as k_coarse_apply, so the two variants agree to the bit.
 template <int D, bool SUB = false>
-__device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s,
-                                                 const bool fuse) {
+__device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, const InstState *st, const int s, const int inst,
+                                                 const int p0, const int p1, const bool fuse) {
   constexpr int D1 = D + 1, NV = D * D1, NWS = kSegThreads / 32;
   __shared__ double wtot[kSegThreads / 32][NV];
   __shared__ double carry[NV];
@@ -389,16 +397,19 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
   __shared__ double ybase[NV];
   __shared__ double ylm[kCoarseMax];
   const int tid = threadIdx.x;
-  const int inst = P.seg_inst[s];
-  if (st[inst].phase == PH_DONE || st[inst].phase == PH_WAIT || st[inst].eval_now) return;
-  const int p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1], len = p1 - p0;
-  const long colbase = (long)P.zoff[inst] - (long)P.pose_off[inst] * NV;
-  const int sl = s - P.seg_begin[inst];
-  const int nco = (fuse && P.c_n[inst] <= kCoarseMax) ? P.c_n[inst] : 0;  // larger coarse spaces: kernels of their own
+  // one round of loads (every address is valid whatever the state says)
+  const int phase = st[inst].phase, evn = st[inst].eval_now;
+  const int zo = P.zoff[inst], po = P.pose_off[inst], po1 = P.pose_off[inst + 1], sb = P.seg_begin[inst];
+  const int cn = P.c_n[inst], coff = P.c_off[inst], cmoff = P.c_moff[inst], cnb = P.c_nb[inst];
+  if (phase == PH_DONE || phase == PH_WAIT || evn) return;
+  const int len = p1 - p0;
+  const long colbase = (long)zo - (long)po * NV;
+  const int sl = s - sb;
+  const int nco = (fuse && cn <= kCoarseMax) ? cn : 0;  // larger coarse spaces: kernels of their own
   if (nco > 0) {
-    const double *__restrict__ Ai = P.c_Ainv + P.c_moff[inst];  // constant during PCG ticks (rebuilt in line-search ticks)
-    const double *cv = P.c_rhs + P.c_off[inst];                  // written by the reverse pass: coherent loads
-    const int nb = P.c_nb[inst], lane = tid & 31, wid = tid >> 5;
+    const double *__restrict__ Ai = P.c_Ainv + cmoff;  // constant during PCG ticks (rebuilt in line-search ticks)
+    const double *cv = P.c_rhs + coff;                  // written by the reverse pass: coherent loads
+    const int nb = cnb, lane = tid & 31, wid = tid >> 5;
     const int row0 = (sl >= 1) ? (sl - 1) * NV : nb, nrow = (sl >= 1) ? NV : nco - nb;
     for (int rr = wid; rr < nrow; rr += NWS) {
       const double *__restrict__ arow = Ai + (size_t)(row0 + rr) * nco;
@@ -411,7 +422,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
   if (tid < NV) carry[tid] = 0.0;
   seg_bar<SUB>();
   if (nco > 0 && sl == 0) {  // landmark block: s = y, partial r.s
-    const int Pi = P.pose_off[inst + 1] - P.pose_off[inst], c0 = P.zoff[inst] + Pi * NV, nlm = nco - P.c_nb[inst];
+    const int Pi = po1 - po, c0 = zo + Pi * NV, nlm = nco - cnb;
     double acc = 0.0;
     for (int j = tid; j < nlm; j += kSegThreads) {
       const double sv = ylm[j];
@@ -476,8 +487,9 @@ __global__ void __launch_bounds__(kSegThreads, D == 2 ? SCORE_PC_MINB : SCORE_PC
   int n_act;
   wl_get(W, WL_RUN, act, n_act);
   for (long long item = blockIdx.x; item < (long long)n_act * W.maxseg; item += gridDim.x) {
-    const int inst = act[item / W.maxseg], s = P.seg_begin[inst] + (int)(item % W.maxseg);
-    if (s < P.seg_begin[inst + 1]) precond_fwd_body<D>(P, V, st, s, fuse);
+    const int inst = act[item / W.maxseg];
+    const int4 sd = P.seg_tab[(size_t)inst * W.maxseg + (int)(item % W.maxseg)];
+    if (sd.x >= 0) precond_fwd_body<D>(P, V, st, sd.z, inst, sd.x, sd.y, fuse);
     __syncthreads();
   }
 }
