@@ -482,8 +482,8 @@ double kernel_bytes_inst(int k, int mode, const InstDims &D) {
                (ls ? 40.0 : 8.0) * nz;
       if (cg || ls) return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 40.0 * nz;
       return 12.0 * nnz + 4.0 * (nz + 1) + 8.0 * m + 8.0 * nz;
-    case KI_PRECOND_REV:  // r, ytmp out, G, M
-      return ev ? 0.0 : 16.0 * nz + 8.0 * Pn * (blk + d1 * d1);
+    case KI_PRECOND_REV:  // r, ytmp out, G, M (symmetric: upper triangle)
+      return ev ? 0.0 : 16.0 * nz + 8.0 * Pn * (blk + d1 * (d1 + 1) / 2);
     case KI_COARSE_APPLY:  // inverse, rhs, solution out, scatter
       return (ev || D.fused) ? 0.0 : 8.0 * (nc * nc + 3.0 * nc);
     case KI_PRECOND_FWD:  // ytmp, r, s out, G (+ fused coarse application: inverse, rhs, scatter)
@@ -1068,7 +1068,7 @@ static int create_impl(const ScoreProblemDesc *desc, int32_t device, ScoreHandle
   DA(P.w, P.m)
   DA(P.b, P.m)
   DA(P.G, (size_t)P.P * blk)
-  DA(P.M, (size_t)P.P * (d + 1) * (d + 1))
+  DA(P.M, (size_t)P.P * ((d + 1) * (d + 2) / 2))  // symmetric blocks, upper triangle
   DA(P.lm_inv, (size_t)P.L * d)
   DA(h->wsum, P.P)
   // index scratch of the incidence-list sort; the assembled CSR pair and its sort scratch are allocated on first use

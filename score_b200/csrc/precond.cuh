@@ -128,7 +128,13 @@ __global__ void k_build_M(DevProblem P, const double *wsum) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.P) return;
   const int d = P.d, d1 = d + 1, blk = P.blk;
-  double *Mp = P.M + (size_t)p * d1 * d1;
+  double Mp[16];                                          // full block, stored below as its upper triangle
+  double *Mout = P.M + (size_t)p * (d1 * (d1 + 1) / 2);  // M_p is symmetric: (d+1)(d+2)/2 doubles, row-major upper
+  auto store = [&]() {
+    int k = 0;
+    for (int i = 0; i < d1; ++i)
+      for (int j = i; j < d1; ++j) Mout[k++] = Mp[i * d1 + j];
+  };
   const int e = P.link_edge[p];
   if (e >= 0) {
     // A = G^{-1} = [[Rg^T, -Rg^T tg],[0,1]] ;  M = A^T D^{-1} A
@@ -151,12 +157,14 @@ __global__ void k_build_M(DevProblem P, const double *wsum) {
         for (int m = 0; m < d1; ++m) acc += A[m * d1 + i] * ((m < d) ? ir : it) * A[m * d1 + j];
         Mp[i * d1 + j] = acc;
       }
+    store();
     return;
   }
   // segment base
   const int inst = find_inst(P.pose_off, P.n_inst, p);
   if (p == P.pose_off[inst]) {  // pinned pose: pin_pose, gurobi_utils.py:316-333
     for (int i = 0; i < d1 * d1; ++i) Mp[i] = 0.0;
+    store();
     return;
   }
   // find the segment end: next pose with link_edge < 0 or instance end
@@ -182,11 +190,13 @@ __global__ void k_build_M(DevProblem P, const double *wsum) {
     if (q > p + 1) sc = 1.0 / (2.0 * P.edge_k[P.link_edge[p + 1]]);
     for (int i = 0; i < d1; ++i)
       for (int j = 0; j < d1; ++j) Mp[i * d1 + j] = (i == j) ? sc : 0.0;
+    store();
     return;
   }
   for (int i = 0; i < d1; ++i) H[i * d1 + i] += 1e-9 * tr;
   spd_inverse(H, d1);
   for (int i = 0; i < d1 * d1; ++i) Mp[i] = H[i];
+  store();
 }
 
 // z0: every segment dead-reckoned from an identity base; landmarks at the origin.
@@ -200,6 +210,36 @@ __global__ void k_init_z(DevProblem P, double *z) {
     z[i] = P.G[(size_t)P.pose_off[inst] * P.blk + loc];
   else
     z[i] = 0.0;
+}
+
+// N doubles of one pose (N even) from / to a 16-byte aligned address: N/2 128-bit accesses.  A thread-per-pose access
+// with a 48- or 96-byte stride touches the same lines either way; half the instructions are half the first-level-cache
+// wavefronts, which is what bounds these kernels (profiles/occupancy_r2.txt).  `al` (CTA-uniform): the address is aligned.
+template <int N>
+__device__ __forceinline__ void ld_block(const double *src, double (&o)[N], const bool al) {
+  if (al && N % 2 == 0) {
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const double2 t = s2[i];
+      o[2 * i] = t.x;
+      o[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = src[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void st_block(double *dst, const double (&v)[N], const bool al) {
+  if (al && N % 2 == 0) {
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) d2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = v[i];
+  }
 }
 
 // Barrier of the kSegThreads threads that run a chain-scan body.  SUB = false: they are the whole CTA.  SUB = true:
@@ -304,6 +344,7 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
   if (phase == PH_DONE || phase == PH_WAIT || evn) return;
   const int len = p1 - p0;
   const long colbase = (long)zo - (long)po * NV;
+  const bool al = (colbase & 1) == 0;  // pose blocks of the column-space vectors start on 16-byte boundaries
   const int slot = s - sb - 1;  // -1: pinned segment
   const bool to_coarse = cn > 0 && slot >= 0;
 
@@ -317,24 +358,19 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
 #pragma unroll
     for (int c = 0; c < NV; ++c) v[c] = 0.0;
     if (valid) {
-      const double *rp = V.r + colbase + (long)pg * NV;
-      const double *Gp = P.G + (size_t)pg * NV;
-      double g[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) g[c] = Gp[c];
+      double g[NV], rv[NV];
+      ld_block<NV>(P.G + (size_t)pg * NV, g, true);
+      ld_block<NV>(V.r + colbase + (long)pg * NV, rv, al);
 #pragma unroll
       for (int r = 0; r < D; ++r) {
-        double rb[D1];
-#pragma unroll
-        for (int c = 0; c < D1; ++c) rb[c] = rp[r * D1 + c];
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          double acc = rb[D] * g[c * D1 + D];
+          double acc = rv[r * D1 + D] * g[c * D1 + D];
 #pragma unroll
-          for (int m = 0; m < D; ++m) acc += rb[m] * g[c * D1 + m];
+          for (int m = 0; m < D; ++m) acc += rv[r * D1 + m] * g[c * D1 + m];
           v[r * D1 + c] = acc;
         }
-        v[r * D1 + D] = rb[D];
+        v[r * D1 + D] = rv[r * D1 + D];
       }
     }
     cta_scan<NV, SUB>(v, wtot, carry);
@@ -344,20 +380,22 @@ __device__ __forceinline__ void precond_rev_body(DevProblem P, SolverVecs V, con
 #pragma unroll
         for (int i = 0; i < NV; ++i) c[i] = v[i];
       } else {
-        const double *Mp = P.M + (size_t)pg * D1 * D1;
-        double mm[D1 * D1];
-#pragma unroll
-        for (int c = 0; c < D1 * D1; ++c) mm[c] = Mp[c];
-        double *yp = V.ytmp + colbase + (long)pg * NV;
+        constexpr int NM = D1 * (D1 + 1) / 2;  // upper triangle of the symmetric M_p
+        double mm[NM], y[NV];
+        ld_block<NM>(P.M + (size_t)pg * NM, mm, true);
 #pragma unroll
         for (int r = 0; r < D; ++r)
 #pragma unroll
           for (int c = 0; c < D1; ++c) {
             double acc = 0.0;
 #pragma unroll
-            for (int m = 0; m < D1; ++m) acc += v[r * D1 + m] * mm[m * D1 + c];
-            yp[r * D1 + c] = acc;
+            for (int m = 0; m < D1; ++m) {
+              const int lo = m < c ? m : c, hi = m < c ? c : m;
+              acc += v[r * D1 + m] * mm[lo * D1 - lo * (lo - 1) / 2 + (hi - lo)];
+            }
+            y[r * D1 + c] = acc;
           }
+        st_block<NV>(V.ytmp + colbase + (long)pg * NV, y, al);
       }
     }
   }
@@ -404,6 +442,7 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
   if (phase == PH_DONE || phase == PH_WAIT || evn) return;
   const int len = p1 - p0;
   const long colbase = (long)zo - (long)po * NV;
+  const bool al = (colbase & 1) == 0;
   const int sl = s - sb;
   const int nco = (fuse && cn <= kCoarseMax) ? cn : 0;  // larger coarse spaces: kernels of their own
   if (nco > 0) {
@@ -447,18 +486,14 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
 #pragma unroll
         for (int c = 0; c < NV; ++c) yp[c] = v[c] = ybase[c];
       } else {
-#pragma unroll
-        for (int c = 0; c < NV; ++c) v[c] = yp[c];
+        ld_block<NV>(yp, v, al);
       }
     }
     cta_scan<NV, SUB>(v, wtot, carry);
     if (valid) {
-      const double *Gp = P.G + (size_t)pg * NV;
-      const double *rp = V.r + colbase + (long)pg * NV;
-      double *sp = V.s + colbase + (long)pg * NV;
-      double g[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) g[c] = Gp[c];
+      double g[NV], rv[NV], sv[NV];
+      ld_block<NV>(P.G + (size_t)pg * NV, g, true);
+      ld_block<NV>(V.r + colbase + (long)pg * NV, rv, al);
 #pragma unroll
       for (int r = 0; r < D; ++r) {
         double tacc = v[r * D1 + D];
@@ -467,13 +502,14 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
           double acc = 0.0;
 #pragma unroll
           for (int m = 0; m < D; ++m) acc += v[r * D1 + m] * g[m * D1 + c];
-          sp[r * D1 + c] = acc;
-          dot += acc * rp[r * D1 + c];
+          sv[r * D1 + c] = acc;
+          dot += acc * rv[r * D1 + c];
           tacc += v[r * D1 + c] * g[c * D1 + D];
         }
-        sp[r * D1 + D] = tacc;
-        dot += tacc * rp[r * D1 + D];
+        sv[r * D1 + D] = tacc;
+        dot += tacc * rv[r * D1 + D];
       }
+      st_block<NV>(V.s + colbase + (long)pg * NV, sv, al);
     }
   }
   const double tot = seg_sum<SUB>(dot, red);
