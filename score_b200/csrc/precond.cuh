@@ -450,12 +450,24 @@ __device__ __forceinline__ void precond_fwd_body(DevProblem P, SolverVecs V, con
     const double *cv = P.c_rhs + coff;                  // written by the reverse pass: coherent loads
     const int nb = cnb, lane = tid & 31, wid = tid >> 5;
     const int row0 = (sl >= 1) ? (sl - 1) * NV : nb, nrow = (sl >= 1) ? NV : nco - nb;
-    for (int rr = wid; rr < nrow; rr += NWS) {
-      const double *__restrict__ arow = Ai + (size_t)(row0 + rr) * nco;
-      double a = 0.0;
-      for (int j = lane; j < nco; j += 32) a += __ldg(arow + j) * cv[j];
-      a = warp_sum(a);
-      if (lane == 0) (sl >= 1 ? ybase : ylm)[rr] = a;
+    // three rows per warp step (rows wid, wid + 4, wid + 8): their loads are all in flight before the first reduction;
+    // every row is still summed lane-strided in j, then by the warp tree
+    constexpr int RW = 3;
+    for (int rr0 = wid; rr0 < nrow; rr0 += RW * NWS) {
+      double a[RW];
+#pragma unroll
+      for (int t = 0; t < RW; ++t) a[t] = 0.0;
+      for (int j = lane; j < nco; j += 32) {
+        const double cj = cv[j];
+#pragma unroll
+        for (int t = 0; t < RW; ++t)
+          if (rr0 + t * NWS < nrow) a[t] += __ldg(Ai + (size_t)(row0 + rr0 + t * NWS) * nco + j) * cj;
+      }
+#pragma unroll
+      for (int t = 0; t < RW; ++t) {
+        const double tot = warp_sum(a[t]);
+        if (lane == 0 && rr0 + t * NWS < nrow) (sl >= 1 ? ybase : ylm)[rr0 + t * NWS] = tot;
+      }
     }
   }
   if (tid < NV) carry[tid] = 0.0;
