@@ -41,12 +41,16 @@ struct InstState {
   int eval_now, want_eval, n_eval, stall;  // true-KKT evaluation ticks
   double alpha, beta, rs, rs0, eta, step;
   int c_age, ls_shift;                     // Newton steps the current coarse inverse has served; line-search ladder shift
-  int fused_cg, pad0;                      // PCG iterations done inside the fused kernel (fused.cuh)
+  int fused_cg, holds;                     // PCG iterations done inside the fused kernel (fused.cuh); stage ends at which
+                                           // the current barrier parameter was held (ctrl_a)
   double mu_c;                             // barrier parameter the coarse inverse was built at
   double mu, mu_ls, dec;                   // barrier parameter (current / used by this tick's line search), Newton decrement
   double mu_out;                           // barrier parameter of the auxiliary variables the last certificate was taken with
   double dec_prev;                         // Newton decrement^2 of the previous step of this barrier stage (0: first step)
   double F, Fmu, kkt, r_stat, r_gap, gnorm, xnorm;
+  // the mu-driven parts of the last certificate (sum lambda s in the gap, min(lambda, s) in the stationarity residual) and
+  // the factor the forcing term has been tightened by while the barrier parameter was held (ctrl_a); 0 reads as 1
+  double gap_mu, stat_mu, eta_scale;
 };
 
 struct DevProblem {

@@ -427,8 +427,25 @@ __device__ __forceinline__ void ctrl_a_body(SolverVecs V, BlockTables T, InstSta
     const double mu_before = S.mu;
     if (S.mu > 0.0 && !retry && (lam2 <= ctol || at_floor || step == 0.0)) {
       if (S.mu <= cfg.mu_eval) S.want_eval = 1;
-      if (S.mu <= cfg.mu_min) S.stall += 1;
-      S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
+      // The certificate's mu-driven parts (sum lambda s in the gap, min(lambda, s) in the stationarity residual) scale
+      // with mu (sqrt(mu)).  Once their estimate at the CURRENT mu — from the last evaluation, taken at mu_out — is a
+      // quarter of the tolerance, what the certificate still lacks is Newton accuracy (its gap term g.z is bounded by
+      // sqrt(decrement * z'Hz)), not a smaller mu: a smaller mu only sharpens the kinks of weakly active range terms and
+      // the inexact Newton iteration stalls on them (sweep instance 4136: decrement stuck at 1e-10 from mu = 1e-10 down
+      // to 1e-16).  So hold mu and tighten the forcing term instead — for up to three stage ends per level: where the
+      // decrement stalls on the kinks themselves (instance 462 at mu = 1e-9) only a smaller mu helps, and the iteration
+      // moves on with the tightened forcing term.
+      const double ratio = (S.mu_out > 0.0) ? S.mu / S.mu_out : 1.0;
+      const bool hold = S.n_eval > 0 && S.mu <= cfg.mu_eval && ratio <= 1.0 && S.gap_mu * ratio <= 0.25 * cfg.kkt_tol &&
+                        S.stat_mu * sqrt(ratio) <= 0.25 * cfg.kkt_tol && S.holds < 3;
+      if (hold) {
+        S.holds += 1;
+        S.eta_scale = fmax(0.3 * (S.eta_scale > 0.0 ? S.eta_scale : 1.0), 1e-2);
+      } else {
+        if (S.mu <= cfg.mu_min) S.stall += 1;
+        S.mu = fmax(S.mu * cfg.mu_factor, cfg.mu_min);
+        S.holds = 0;
+      }
     }
     S.dec_prev = (S.mu != mu_before) ? 0.0 : S.dec;
     if (S.mu == 0.0) S.want_eval = 1;
@@ -675,6 +692,8 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
     S.xnorm = sqrt(zz + dn2);
     S.r_stat = S.gnorm / (1.0 + S.xnorm);
     S.r_gap = fabs(pd) / (1.0 + fabs(F) + fabs(F - pd));
+    S.gap_mu = fabs(gsum) / (1.0 + fabs(F) + fabs(F - pd));
+    S.stat_mu = sqrt(ssum) / (1.0 + S.xnorm);
     S.mu_out = S.mu_ls;
     S.kkt = fmax(S.r_stat, S.r_gap);
     S.n_eval += 1;
@@ -739,7 +758,8 @@ __device__ __forceinline__ void ctrl_b_body(DevProblem P, SolverVecs V, BlockTab
   S.dec = 0.0;
   // inexact-Newton forcing term: tighter on the last barrier stages (the certificate needs the accuracy) and right
   // after a line search that found no decrease (the direction was too inexact to be a descent direction)
-  S.eta = cfg.forcing * ((S.mu <= cfg.mu_eval) ? 0.3 : 1.0) * ((S.step == 0.0 && S.newton_it > 0) ? 0.1 : 1.0);
+  S.eta = cfg.forcing * ((S.mu <= cfg.mu_eval) ? 0.3 : 1.0) * ((S.step == 0.0 && S.newton_it > 0) ? 0.1 : 1.0) *
+          (S.eta_scale > 0.0 ? S.eta_scale : 1.0);
   if (S.want_eval || !(rs_new > 0.0) || S.newton_it >= cfg.max_newton || !isfinite(Fmu)) S.eval_now = 1;
   S.want_eval = 0;
 }

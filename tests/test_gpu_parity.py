@@ -651,3 +651,24 @@ def test_dynamic_sweep_queue_matches_plain_solve_bitwise(built_lib):
         assert np.array_equal(arrs[1], ref[1][batch.pose_off[a]:batch.pose_off[b]])
         assert np.array_equal(arrs[2], ref[2][batch.lm_off[a]:batch.lm_off[b]])
         assert np.array_equal(arrs[3], ref[3][batch.rng_off[a]:batch.rng_off[b]])
+
+
+@pytest.mark.parametrize("index", [462, 4136])
+def test_weakly_active_sweep_instances_certify(built_lib, index):
+    """Two Monte-Carlo sweep instances whose optimum has weakly active range terms (the Newton decrement stalls on their
+    kinks: 4136 needs a tighter forcing term at a held barrier parameter, 462 a smaller barrier parameter): both must
+    reach the 1e-6 certificate, and the oracle's evaluator must agree on the returned point."""
+    from oracle import score_oracle as so
+    from score_b200 import generators
+    from score_b200.lowering import lower_manhattan_arrays
+    from score_b200.solver import ScoreSolver
+
+    seed = generators.MC_BASE_SEED + index
+    prob = lower_manhattan_arrays(generators.manhattan_2d_arrays(seed, n_robots=20, n_steps=100), "QCQP", with_names=False)
+    with ScoreSolver(prob) as s:
+        st = s.solve()
+        poses, _, lms, dist = s.solution()
+    assert st.n_solved == 1 and st.instances[0]["rel_kkt"] <= 1e-6
+    op = so.assemble(generators.manhattan_2d(seed, n_robots=20, n_steps=100), so.QCQP)
+    x = _full_x(op, poses, lms, dist)
+    assert so.kkt_qcqp(op, x)["rel_kkt"] <= 1.5e-6  # tolerance of the test: the device's 1e-6 plus evaluator rounding
