@@ -188,7 +188,9 @@ class SweepQueue:
     def run(self, steps: int, costs: Optional[Sequence[float]] = None) -> List[tuple]:
         """Work through this run's queue together with the other ranks (every rank must call ``run`` the same number
         of times with the same ``steps`` / ``costs``).  Returns the jobs THIS rank ran as (step, part, result), in
-        completion order; returns when the queue is empty and this rank's last job has finished."""
+        completion order; returns when the queue is empty and this rank's last job has finished.  A rank that returns
+        early must keep the counter's store alive until the others are done: put a barrier between the last ``run``
+        and ``destroy_process_group`` (the store is served by rank 0)."""
         from concurrent.futures import ThreadPoolExecutor
 
         order = self.job_order(costs, self.n_parts)

@@ -167,6 +167,7 @@ def _queue_worker(rank, world, port, out):
             for _ in range(2):
                 dist.barrier()
                 runs.append(q.run(5, [1, 6, 2, 5, 3, 4]))
+            dist.barrier()  # the store lives in rank 0: it must not go away while the slow rank still claims jobs
         out.put((rank, runs))
     finally:
         dist.destroy_process_group()
