@@ -1453,6 +1453,22 @@ static bool coarse_apply_split() {
   return split;
 }
 
+// Wait for a cycle's completion event.  A single graph's cycle is a few hundred microseconds: polled, the host sees it
+// end within a microsecond; a batch's cycle is milliseconds: after SCORE_SPIN_US of polling the thread sleeps on the
+// (blocking-sync) event, so the 4-6 solves a sweep keeps in flight per GPU do not each burn a host core.
+#ifndef SCORE_SPIN_US
+#define SCORE_SPIN_US 150
+#endif
+static cudaError_t wait_event_hybrid(cudaEvent_t ev) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(SCORE_SPIN_US)) break;
+  }
+  return cudaEventSynchronize(ev);
+}
+
 // Preconditioner application s = P r (+ partial r.s), shared by the line-search and PCG ticks.
 template <int D>
 static int launch_precond(ScoreHandle_ *h, cudaStream_t st, TickProfiler *pf) {
@@ -2020,7 +2036,7 @@ extern "C" int score_solve(ScoreHandle h, const ScoreParams *params, ScoreStats 
     cycles += 1;
     // the completion count of the previous cycle is read while this one runs (no host bubble between cycles)
     if (cycles >= 2) {
-      SCORE_CUDA_CHECK(cudaEventSynchronize(h->ev_done[slot ^ 1]));
+      SCORE_CUDA_CHECK(wait_event_hybrid(h->ev_done[slot ^ 1]));
       last_done = h->h_ndone[slot ^ 1];
       if (last_done >= P.n_inst) break;
     }
