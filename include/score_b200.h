@@ -198,8 +198,12 @@ int score_comm_init(ScoreHandle h, int32_t n_ranks, int32_t rank, const char *id
  *   SCORE_INT_RANGE_CURV  K_inst x d(d+1)/2 curvature blocks 2 w H_k of the range terms (upper, row-major)
  *   SCORE_INT_FRAMES      P_inst x d x (d+1) dead-reckoned frames of the odometry-chain preconditioner
  *   SCORE_INT_TRACE       (only after a solve with ScoreParams.verbose >= 2) 256 x 8 doubles, one record per Newton
- *                         step: barrier parameter, step length, PCG iterations, decrement^2, F_mu, r.s, ladder shift, eta */
-enum { SCORE_INT_COARSE_INV = 0, SCORE_INT_RANGE_CURV = 1, SCORE_INT_FRAMES = 2, SCORE_INT_TRACE = 3 };
+ *                         step: barrier parameter, step length, PCG iterations, decrement^2, F_mu, r.s, ladder shift, eta  *   SCORE_INT_REF_GRAD / _DIR / _HDIR / _DIAG  (after score_refine) tangent-space vectors of the refinement in the
+ *                         column-space slots of the instance (pose p: first dof entries of its block, then landmarks):
+ *                         gradient J^T W r of the last linearisation, last PCG direction p, (J^T W J + lambda D) p, D
+ */
+enum { SCORE_INT_COARSE_INV = 0, SCORE_INT_RANGE_CURV = 1, SCORE_INT_FRAMES = 2, SCORE_INT_TRACE = 3, SCORE_INT_REF_GRAD = 4,
+       SCORE_INT_REF_DIR = 5, SCORE_INT_REF_HDIR = 6, SCORE_INT_REF_DIAG = 7 };
 int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, double *out, int64_t capacity, int64_t *count);
 
 /* Stand-alone SO(d) rounding of n d x d matrices (host pointers) on the device:
@@ -224,6 +228,39 @@ int score_trajectory_ate(int32_t dim, int32_t n_traj, const int32_t *traj_off, c
  * NULL = one trajectory per instance (n_traj is then ignored).  gt_pos: [P*dim] host. */
 int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj_off, const double *gt_pos, int32_t align,
                    double *rmse, double *R, double *t);
+
+/* Local refinement after the relaxation (/root/reference/README.md:63-67: SCORE's estimate is
+ * the initialisation of a local search — GTSAM in the paper).  Batched Levenberg-Marquardt on the original non-convex
+ * cost (the reference's objective, gurobi_utils.py:358-526, with R_p in SO(d) and the distance variables eliminated:
+ * ranges enter as w (||p_a - p_b|| - r)^2), first pose of every instance fixed; Gauss-Newton systems by block-Jacobi
+ * PCG, matrix-free over the factor incidence lists.  Starts from the rounded solution of the last score_solve (rotations
+ * rounded, translations and landmarks as relaxed), or from init_poses [P*d*(d+1)] ([R|t] row-major, R in SO(d)) and
+ * init_landmarks [L*d] when both are given (host or device pointers).  Call after score_solve (the handle's factor
+ * lists are built there).  No reference counterpart in /root/reference itself. */
+typedef struct ScoreRefineParams {
+  int32_t max_outer;  /* Levenberg-Marquardt iterations per instance, <=0: 100 */
+  int32_t max_inner;  /* PCG iterations per Gauss-Newton system, <=0: 200 */
+  double rel_tol;     /* stop when an accepted step lowers the cost by less than rel_tol (1 + cost), <=0: 1e-10 */
+  double lambda0;     /* initial damping lambda of (J'WJ + lambda I), <=0: 1e-3 */
+  double cg_tol;      /* PCG relative residual (preconditioned norm), <=0: 1e-4 (looser solves were seen to end in
+                         other, worse local minima than an exact Levenberg-Marquardt iteration) */
+  void *stream;       /* cudaStream_t, NULL: the handle's own stream */
+} ScoreRefineParams;
+typedef struct ScoreRefineStats {
+  int32_t n_instances;
+  int32_t n_converged;      /* instances that stopped by rel_tol (or at a stationary point), not by max_outer */
+  int32_t outer_iterations; /* Levenberg-Marquardt iterations the batch ran (the slowest instance's) */
+  int32_t kernel_launches;
+  double refine_ms;
+} ScoreRefineStats;
+typedef struct ScoreRefineInstanceStats {
+  double cost_initial, cost_final;
+  int32_t outer_iterations, accepted_steps;
+} ScoreRefineInstanceStats;
+int score_refine(ScoreHandle h, const ScoreRefineParams *params, const double *init_poses, const double *init_landmarks,
+                 ScoreRefineStats *stats, ScoreRefineInstanceStats *per_instance);
+/* Refined estimate: poses [P*d*(d+1)] as [R|t] row-major with R in SO(d), landmarks [L*d] (host buffers). */
+int score_get_refined(ScoreHandle h, double *poses, double *landmarks);
 
 void score_destroy(ScoreHandle h);
 /* Handles take their device memory, stream and events from process-wide caches that score_destroy refills (so

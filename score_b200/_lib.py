@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("SCORE_B200_LIB") or os.path.join(_HERE, "libscore_b20
 SCORE_RELAX_QCQP, SCORE_RELAX_SOCP = 0, 1
 SCORE_CSR_FULL, SCORE_CSR_REDUCED, SCORE_CSR_REDUCED_T = 0, 1, 2
 SCORE_INT_COARSE_INV, SCORE_INT_RANGE_CURV, SCORE_INT_FRAMES, SCORE_INT_TRACE = 0, 1, 2, 3
+SCORE_INT_REF_GRAD, SCORE_INT_REF_DIR, SCORE_INT_REF_HDIR, SCORE_INT_REF_DIAG = 4, 5, 6, 7
 SCORE_OK, SCORE_ERR_INVALID, SCORE_ERR_CUDA, SCORE_ERR_STATE, SCORE_ERR_ALLOC = 0, -1, -2, -3, -4
 
 _i32p = C.POINTER(C.c_int32)
@@ -125,6 +126,36 @@ class ScoreStats(C.Structure):
     ]
 
 
+class ScoreRefineParams(C.Structure):
+    _fields_ = [
+        ("max_outer", C.c_int32),
+        ("max_inner", C.c_int32),
+        ("rel_tol", C.c_double),
+        ("lambda0", C.c_double),
+        ("cg_tol", C.c_double),
+        ("stream", C.c_void_p),
+    ]
+
+
+class ScoreRefineStats(C.Structure):
+    _fields_ = [
+        ("n_instances", C.c_int32),
+        ("n_converged", C.c_int32),
+        ("outer_iterations", C.c_int32),
+        ("kernel_launches", C.c_int32),
+        ("refine_ms", C.c_double),
+    ]
+
+
+class ScoreRefineInstanceStats(C.Structure):
+    _fields_ = [
+        ("cost_initial", C.c_double),
+        ("cost_final", C.c_double),
+        ("outer_iterations", C.c_int32),
+        ("accepted_steps", C.c_int32),
+    ]
+
+
 EXPORTED_SYMBOLS = [
     "score_create",
     "score_solve",
@@ -137,6 +168,8 @@ EXPORTED_SYMBOLS = [
     "score_round_so",
     "score_trajectory_ate",
     "score_eval_ate",
+    "score_refine",
+    "score_get_refined",
     "score_destroy",
     "score_release_cached",
     "score_last_error",
@@ -197,6 +230,11 @@ def load() -> C.CDLL:
     lib.score_eval_ate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p]
     lib.score_eval_ate.restype = C.c_int
+    lib.score_refine.argtypes = [C.c_void_p, C.POINTER(ScoreRefineParams), C.c_void_p, C.c_void_p,
+                                 C.POINTER(ScoreRefineStats), C.c_void_p]
+    lib.score_refine.restype = C.c_int
+    lib.score_get_refined.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.score_get_refined.restype = C.c_int
     lib.score_destroy.argtypes = [C.c_void_p]
     lib.score_destroy.restype = None
     lib.score_release_cached.argtypes = []

@@ -22,6 +22,7 @@
 #include "fused.cuh"
 #include "hessvec.cuh"
 #include "precond.cuh"
+#include "refine.cuh"
 #include "solver.cuh"
 
 #ifndef SCORE_EVENT_SYNC_FLAG
@@ -91,6 +92,9 @@ struct ScoreHandle_ {
   std::vector<int> pose_off, lm_off, edge_off, rng_off, prior_off, zoff, roff, nnzoff, seg_begin;
   std::vector<int> rb_begin, cb_begin, pb_begin;
   int n_pbd = 0;  // entries of the dense Hessian-vector item table
+  RefVecs R{};    // local refinement (refine.cuh): allocated by the first score_refine
+  bool ref_alloc = false, refined = false;
+  int *ref_ndone = nullptr;
   void *inc_tmp = nullptr;  // radix-sort scratch of the incidence lists
   uint4 *inc_in = nullptr;  // unsorted incidence records
   size_t inc_tmp_bytes = 0;
@@ -620,6 +624,171 @@ extern "C" int score_eval_ate(ScoreHandle h, int32_t n_traj, const int32_t *traj
     rc = ate_launch(P.d, n_traj, d_off, h->out_poses, P.blk, P.d + 1, P.d, d_gt, align, rmse, R, t, nullptr);
   SCORE_CUDA_CHECK(e);
   return rc;
+}
+
+// ---- local refinement (refine.cuh)
+template <int D>
+static int refine_run(ScoreHandle_ *h, const RefCfg &cfg, cudaStream_t st, int *launches, int *outer_done) {
+  const DevProblem &P = h->P;
+  const RefVecs &R = h->R;
+  const BlockTables &T = h->T;
+  const int nb = T.n_pb, ni = P.n_inst, cgrid = (ni + 3) / 4;
+  int n = 0;
+  k_ref_visit<D, RM_COST><<<nb, kThreads, 0, st>>>(P, R, T, 0);
+  k_ref_ctrl<RC_COST0><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+  n += 2;
+  int done = 0, outer = 0;
+  for (; outer < cfg.max_outer && done < ni; ++outer) {
+    k_ref_visit<D, RM_LIN><<<nb, kThreads, 0, st>>>(P, R, T, 0);
+    k_ref_vec<D, RV_START><<<nb, kThreads, 0, st>>>(P, R, T);
+    SCORE_CUDA_CHECK(cudaMemsetAsync(h->ref_ndone + 1, 0, sizeof(int), st));
+    k_ref_ctrl<RC_START><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+    n += 3;
+    int cg_ended = 0;
+    for (int it = 0; it < cfg.max_inner; ++it) {
+      if (it > 0 && (it & 15) == 0) {  // every 16 PCG iterations: have all instances' solves ended?
+        SCORE_CUDA_CHECK(cudaMemcpyAsync(&cg_ended, h->ref_ndone + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (cg_ended + done >= ni) break;
+      }
+      k_ref_visit<D, RM_HV><<<nb, kThreads, 0, st>>>(P, R, T, 0);
+      k_ref_ctrl<RC_ALPHA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+      k_ref_vec<D, RV_UPDATE><<<nb, kThreads, 0, st>>>(P, R, T);
+      k_ref_ctrl<RC_BETA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+      k_ref_vec<D, RV_PUPDATE><<<nb, kThreads, 0, st>>>(P, R, T);
+      n += 5;
+    }
+    k_ref_vec<D, RV_TRIAL><<<nb, kThreads, 0, st>>>(P, R, T);
+    k_ref_visit<D, RM_COST><<<nb, kThreads, 0, st>>>(P, R, T, 1);
+    k_ref_ctrl<RC_ACCEPT><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+    k_ref_commit<D><<<nb, kThreads, 0, st>>>(P, R, T);
+    k_ref_clear<<<grid_for(ni, 128), 128, 0, st>>>(R, ni);
+    n += 5;
+    SCORE_CUDA_CHECK(cudaMemcpyAsync(&done, h->ref_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  SCORE_CUDA_CHECK(cudaGetLastError());
+  *launches = n;
+  *outer_done = outer;
+  return SCORE_OK;
+}
+
+extern "C" int score_refine(ScoreHandle h, const ScoreRefineParams *params, const double *init_poses,
+                            const double *init_landmarks, ScoreRefineStats *stats, ScoreRefineInstanceStats *per_instance) {
+  if (!h) {
+    g_score_last_error = "null handle";
+    return SCORE_ERR_INVALID;
+  }
+  if (!h->solved_once) {
+    g_score_last_error = "score_refine called before score_solve (the factor incidence lists are built there)";
+    return SCORE_ERR_STATE;
+  }
+  if ((init_poses == nullptr) != (init_landmarks == nullptr) && h->P.L > 0) {
+    g_score_last_error = "score_refine: give both init_poses and init_landmarks, or neither";
+    return SCORE_ERR_INVALID;
+  }
+  ScoreRefineParams prm{};
+  if (params) prm = *params;
+  RefCfg cfg;
+  cfg.max_outer = prm.max_outer > 0 ? prm.max_outer : 100;
+  cfg.max_inner = prm.max_inner > 0 ? prm.max_inner : 200;
+  cfg.rel_tol = prm.rel_tol > 0 ? prm.rel_tol : 1e-10;
+  cfg.lambda0 = prm.lambda0 > 0 ? prm.lambda0 : 1e-3;
+  cfg.eta = prm.cg_tol > 0 ? prm.cg_tol : 1e-4;
+  SCORE_CUDA_CHECK(cudaSetDevice(h->device));
+  const DevProblem &P = h->P;
+  const int d = P.d, dof = d + (d == 2 ? 1 : 3);
+  int rc;
+  if (!h->ref_alloc) {
+    RefVecs &R = h->R;
+#define RA(ptr, n) \
+  if ((rc = dalloc(h, &(ptr), (size_t)(n)))) return rc;
+    RA(R.x, P.nz) RA(R.xt, P.nz) RA(R.g, P.nz) RA(R.dg, P.nz) RA(R.dl, P.nz) RA(R.r, P.nz) RA(R.s, P.nz) RA(R.p, P.nz)
+    RA(R.q, P.nz)
+    const size_t nblk = (size_t)P.P * dof * dof + (size_t)P.L * d * d;
+    RA(R.Db, nblk) RA(R.Mi, nblk) RA(R.part_cost, h->T.n_pb) RA(R.part_dot, h->T.n_pb) RA(R.part_aux, 2 * (size_t)h->T.n_pb) RA(R.st, P.n_inst)
+    RA(h->ref_ndone, 2)
+#undef RA
+    h->ref_alloc = true;
+  }
+  cudaStream_t st = prm.stream ? (cudaStream_t)prm.stream : h->own_stream;
+  h->last_stream = st;
+  struct TimingPair {  // two pooled timing events, returned to the pool on every exit path
+    cudaEvent_t e[2] = {};
+    int dev = 0;
+    ~TimingPair() {
+      for (auto x : e)
+        if (x) g_cache.put_tevent(dev, x);
+    }
+  } tp;
+  tp.dev = h->device;
+  cudaEvent_t *ev = tp.e;
+  for (int i = 0; i < 2; ++i) SCORE_CUDA_CHECK(g_cache.get_tevent(h->device, &ev[i]));
+  SCORE_CUDA_CHECK(cudaEventRecord(ev[0], st));
+  SCORE_CUDA_CHECK(cudaMemsetAsync(h->ref_ndone, 0, 2 * sizeof(int), st));
+  DevBuf ip, il;
+  const double *d_poses = h->out_poses, *d_round = h->out_round, *d_lms = h->out_lms;
+  if (init_poses) {
+    SCORE_CUDA_CHECK(ip.alloc(sizeof(double) * std::max<size_t>(1, (size_t)P.P * P.blk)));
+    SCORE_CUDA_CHECK(il.alloc(sizeof(double) * std::max<size_t>(1, (size_t)P.L * d)));
+    SCORE_CUDA_CHECK(cudaMemcpyAsync(ip.as<double>(), init_poses, sizeof(double) * (size_t)P.P * P.blk, cudaMemcpyDefault, st));
+    if (P.L > 0)
+      SCORE_CUDA_CHECK(cudaMemcpyAsync(il.as<double>(), init_landmarks, sizeof(double) * (size_t)P.L * d, cudaMemcpyDefault, st));
+    d_poses = ip.as<double>();
+    d_round = nullptr;
+    d_lms = il.as<double>();
+  }
+  k_ref_init<<<grid_for(P.nz, 256), 256, 0, st>>>(P, h->R, d_poses, d_round, d_lms, cfg.lambda0);
+  int launches = 0, outer = 0;
+  rc = (d == 2) ? refine_run<2>(h, cfg, st, &launches, &outer) : refine_run<3>(h, cfg, st, &launches, &outer);
+  if (rc) return rc;
+  SCORE_CUDA_CHECK(cudaEventRecord(ev[1], st));
+  SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<RefState> hs(P.n_inst);
+  SCORE_CUDA_CHECK(cudaMemcpy(hs.data(), h->R.st, sizeof(RefState) * P.n_inst, cudaMemcpyDeviceToHost));
+  int conv = 0;
+  for (int i = 0; i < P.n_inst; ++i) {
+    conv += hs[i].converged ? 1 : 0;
+    if (per_instance) {
+      per_instance[i].cost_initial = hs[i].cost0;
+      per_instance[i].cost_final = hs[i].cost;
+      per_instance[i].outer_iterations = hs[i].outer;
+      per_instance[i].accepted_steps = hs[i].n_accept;
+    }
+  }
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    stats->n_instances = P.n_inst;
+    stats->n_converged = conv;
+    stats->outer_iterations = outer;
+    stats->kernel_launches = launches + 1;
+    stats->refine_ms = ms;
+  }
+  h->refined = true;
+  return SCORE_OK;
+}
+
+extern "C" int score_get_refined(ScoreHandle h, double *poses, double *landmarks) {
+  if (!h) {
+    g_score_last_error = "null handle";
+    return SCORE_ERR_INVALID;
+  }
+  if (!h->refined) {
+    g_score_last_error = "score_get_refined called before score_refine";
+    return SCORE_ERR_STATE;
+  }
+  SCORE_CUDA_CHECK(cudaSetDevice(h->device));
+  const DevProblem &P = h->P;
+  // the state is in column-space layout: instance by instance, pose blocks then landmarks
+  std::vector<double> x(P.nz);
+  SCORE_CUDA_CHECK(cudaMemcpy(x.data(), h->R.x, sizeof(double) * P.nz, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < P.n_inst; ++i) {
+    const size_t z0 = h->zoff[i], Pi = h->pose_off[i + 1] - h->pose_off[i], Li = h->lm_off[i + 1] - h->lm_off[i];
+    if (poses) memcpy(poses + (size_t)h->pose_off[i] * P.blk, x.data() + z0, sizeof(double) * Pi * P.blk);
+    if (landmarks && Li) memcpy(landmarks + (size_t)h->lm_off[i] * P.d, x.data() + z0 + Pi * P.blk, sizeof(double) * Li * P.d);
+  }
+  return SCORE_OK;
 }
 
 // Pinned host slots for the per-handle completion counters.  cudaMallocHost / cudaFreeHost are device-wide
@@ -2360,6 +2529,18 @@ extern "C" int score_get_internal(ScoreHandle h, int32_t which, int32_t inst, do
     case SCORE_INT_TRACE:
       n = h->V.trace ? (int64_t)h->V.trace_cap * kTraceRec : 0;
       src = h->V.trace ? h->V.trace + (size_t)inst * h->V.trace_cap * kTraceRec : nullptr;
+      break;
+    case SCORE_INT_REF_GRAD:
+    case SCORE_INT_REF_DIR:
+    case SCORE_INT_REF_HDIR:
+    case SCORE_INT_REF_DIAG:
+      if (!h->refined) {
+        g_score_last_error = "refinement internals exist only after score_refine";
+        return SCORE_ERR_STATE;
+      }
+      n = h->zoff[inst + 1] - h->zoff[inst];
+      src = (which == SCORE_INT_REF_GRAD ? h->R.g : which == SCORE_INT_REF_DIR ? h->R.p : which == SCORE_INT_REF_HDIR ? h->R.q : h->R.dg) +
+            h->zoff[inst];
       break;
     default:
       g_score_last_error = "unknown internal array selector";

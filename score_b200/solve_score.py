@@ -135,6 +135,47 @@ def solve_score_batch(datas: Sequence[FactorGraphData], relaxation_type: str = Q
     return (out, stats) if return_stats else out
 
 
+def solve_and_refine(datas: Sequence[FactorGraphData], relaxation_type: str = QCQP_RELAXATION, device: int = 0,
+                     kkt_tol: float = DEFAULT_KKT_TOL, refine_kw: Optional[dict] = None, **solver_kw):
+    """SCORE as the initialisation of a local search (/root/reference/README.md:63-67; the paper uses GTSAM for the
+    second step): solve the relaxation of every instance as one batch, then refine the rounded estimates on the original
+    non-convex cost on the same GPU (``score_refine``: batched Levenberg-Marquardt, csrc/refine.cuh).
+
+    Returns (relaxed, refined, records): two lists of ``SolverResults`` in input order (the refined ones carry the
+    refined poses / landmarks; their distance variables are the unit directions (QCQP) or lengths (SOCP) between the
+    refined endpoints; ``solver_cost`` is the non-convex cost) and the per-instance refinement records."""
+    check_valid_relaxation(relaxation_type)
+    for data in datas:
+        _check_factor_graph(data)
+    prob = concat([lower_factor_graph(data, relaxation_type) for data in datas])
+    d = prob.dim
+    with ScoreSolver(prob, device=device) as solver:
+        stats = solver.solve(kkt_tol=kkt_tol, **solver_kw)
+        poses, rounded, lms, dist = solver.solution()
+        rec, rstats = solver.refine(**(refine_kw or {}))
+        rposes, rlms = solver.refined()
+    # distance variables of the refined point: what the eliminated variable equals there
+    owners = []
+    for i in range(prob.n_instances):
+        p0, p1, l0, l1 = prob.pose_off[i], prob.pose_off[i + 1], prob.lm_off[i], prob.lm_off[i + 1]
+        own = np.concatenate([rposes[p0:p1, :, d], rlms[l0:l1]], axis=0)
+        k0, k1 = prob.rng_off[i], prob.rng_off[i + 1]
+        diff = own[prob.rng_a[k0:k1]] - own[prob.rng_b[k0:k1]]
+        n = np.linalg.norm(diff, axis=1, keepdims=True)
+        owners.append(diff / np.maximum(n, 1e-300) if relaxation_type == QCQP_RELAXATION else n)
+    rdist = np.concatenate(owners, axis=0) if owners else dist
+    relaxed, refined = [], []
+    for i, data in enumerate(datas):
+        r = stats.instances[i]
+        per = stats.total_ms * 1e-3 / len(datas)
+        relaxed.append(pack_results(prob, i, poses, rounded, lms, dist, per, r["solved"], data.get_pose_chain_names(),
+                                    float(r["objective"])))
+        refined.append(pack_results(prob, i, rposes, np.ascontiguousarray(rposes[:, :, :d]), rlms, rdist,
+                                    per + rstats["refine_ms"] * 1e-3 / len(datas), r["solved"], data.get_pose_chain_names(),
+                                    float(rec[i]["cost_final"])))
+    return relaxed, refined, rec
+
+
 def solve_problem_with_intermediate_iterates(data: FactorGraphData, relaxation_type: str = QCQP_RELAXATION,
                                              device: int = 0, max_iterates: int = 1000) -> List[SolverResults]:
     """solve_score.py:89-116: the reference re-solves with BarIterLimit = 0, 1, 2, ... and collects

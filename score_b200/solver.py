@@ -54,6 +54,9 @@ _INST_DTYPE = np.dtype(
     ]
 )
 
+_REFINE_DTYPE = np.dtype([("cost_initial", np.float64), ("cost_final", np.float64), ("outer_iterations", np.int32),
+                          ("accepted_steps", np.int32)])
+
 
 def _check(rc: int) -> None:
     if rc == 0:
@@ -227,6 +230,36 @@ class ScoreSolver:
         _check(self._lib.score_eval_ate(self._h, n, None if off is None else off.ctypes.data, gt.ctypes.data,
                                         1 if align else 0, rmse.ctypes.data, R.ctypes.data, t.ctypes.data))
         return rmse, R, t
+
+    def refine(self, max_outer: int = 0, max_inner: int = 0, rel_tol: float = 0.0, lambda0: float = 0.0, cg_tol: float = 0.0,
+               init=None):
+        """Local refinement of the last solve's rounded estimate on the original non-convex cost (score_refine: batched
+        Levenberg-Marquardt, /root/reference/README.md:63-67 — the step the paper hands to GTSAM).  ``init``: optional
+        (poses [P, d, d+1] as [R|t] with R in SO(d), landmarks [L, d]) to start from instead.  Returns
+        (per-instance record array: cost_initial, cost_final, outer_iterations, accepted_steps; stats dict); the refined
+        estimate is read with ``refined()``."""
+        p = self.prob
+        prm = _lib.ScoreRefineParams()
+        prm.max_outer, prm.max_inner = max_outer, max_inner
+        prm.rel_tol, prm.lambda0, prm.cg_tol = rel_tol, lambda0, cg_tol
+        st = _lib.ScoreRefineStats()
+        inst = np.zeros(p.n_instances, dtype=_REFINE_DTYPE)
+        ip = il = None
+        if init is not None:
+            ip, il = _f64(init[0]), _f64(init[1])
+            if ip.shape != (p.P, p.dim, p.dim + 1) or il.shape != (p.L, p.dim):
+                raise ValueError(f"init must be (poses {(p.P, p.dim, p.dim + 1)}, landmarks {(p.L, p.dim)})")
+        _check(self._lib.score_refine(self._h, C.byref(prm), None if ip is None else ip.ctypes.data,
+                                      None if il is None else il.ctypes.data, C.byref(st), inst.ctypes.data))
+        return inst, {"n_converged": int(st.n_converged), "outer_iterations": int(st.outer_iterations),
+                      "kernel_launches": int(st.kernel_launches), "refine_ms": float(st.refine_ms)}
+
+    def refined(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(poses [P, d, d+1] as [R|t] with R in SO(d), landmarks [L, d]) after ``refine``."""
+        p = self.prob
+        poses, lms = np.empty((p.P, p.dim, p.dim + 1)), np.empty((p.L, p.dim))
+        _check(self._lib.score_get_refined(self._h, poses.ctypes.data, lms.ctypes.data if p.L else None))
+        return poses, lms
 
     def internal(self, which: int, inst: int = 0) -> np.ndarray:
         """Solver internals of one instance (score_get_internal): flat float64 array."""

@@ -1,0 +1,162 @@
+"""Local refinement after the relaxation: score_refine against the CPU restatement of its cost
+(oracle/refine_oracle.py) and scipy.optimize.least_squares from the same start."""
+import numpy as np
+import pytest
+
+
+def _graph(d, seed=3):
+    from score_b200 import generators
+    from score_b200.lowering import lower_grid3d_arrays, lower_manhattan_arrays
+
+    if d == 2:
+        arr = generators.manhattan_2d_arrays(generators.MC_BASE_SEED + seed, n_robots=3, n_steps=14)
+        return lower_manhattan_arrays(arr, "QCQP", with_names=False), arr
+    arr = generators.grid_3d_arrays(seed, n_robots=3, n_steps=10, grid=6, n_landmarks=4, n_ranges=90)
+    return lower_grid3d_arrays(arr), arr
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_refine_oracle_cost_is_the_reference_objective_on_so_d(d):
+    """CPU only: on a point with R in SO(d) the refinement cost equals the reference's relaxed objective minimised over
+    the distance variables (the range part: w max(0, n - r)^2 relaxed vs w (n - r)^2 here, equal when n >= r)."""
+    from oracle import refine_oracle as ro
+    from oracle import score_oracle as so
+
+    prob, _ = _graph(d)
+    rng = np.random.default_rng(0)
+    P, L = prob.P, prob.L
+    poses = np.zeros((P, d, d + 1))
+    for p in range(P):
+        poses[p, :, :d] = ro.exp_so(rng.normal(size=1 if d == 2 else 3), d)
+        poses[p, :, d] = rng.normal(size=d) * 3
+    lms = rng.normal(size=(L, d)) * 3
+    f = ro.cost(prob, poses, lms)
+    r = ro.residuals(prob, poses, lms)
+    assert r.shape[0] == prob.E * (d + d * d) + prob.K + prob.Lp * d and np.isclose(f, r @ r)
+    # gradient check of the tangent parametrisation: directional derivative by finite differences
+    g = ro.tangent_gradient(prob, poses, lms)
+    xi = rng.normal(size=g.shape) * 1e-5
+    f1 = ro.cost(prob, *ro._retract(prob, poses, lms, xi))
+    assert abs((f1 - f) - 2 * g @ xi) <= 1e-3 * abs(2 * g @ xi) + 1e-9 * (1 + f)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [2, 3])
+def test_refine_reaches_a_stationary_point_and_matches_least_squares(built_lib, d):
+    from oracle import refine_oracle as ro
+    from score_b200.solver import ScoreSolver
+
+    prob, _ = _graph(d)
+    with ScoreSolver(prob) as s:
+        st = s.solve()
+        assert st.n_solved == 1
+        relaxed, rounded, lms0, _ = s.solution()
+        rec, stats = s.refine()
+        poses, lms = s.refined()
+    poses0 = relaxed.copy()
+    poses0[:, :, :d] = rounded  # the start the device used: rounded rotations, relaxed translations / landmarks
+    f0 = ro.cost(prob, poses0, lms0)
+    f1 = ro.cost(prob, poses, lms)
+    assert stats["n_converged"] == 1 and rec["accepted_steps"][0] >= 1
+    assert np.isclose(rec["cost_initial"][0], f0, rtol=1e-9) and np.isclose(rec["cost_final"][0], f1, rtol=1e-9)
+    assert f1 < f0
+    # rotations stay in SO(d); the pinned pose does not move
+    R = poses[:, :, :d]
+    assert np.abs(R @ np.transpose(R, (0, 2, 1)) - np.eye(d)).max() < 1e-10 and np.all(np.linalg.det(R) > 0.999)
+    assert np.array_equal(poses[0], poses0[0])
+    # first-order optimality in the tangent coordinates
+    g = ro.tangent_gradient(prob, poses, lms)
+    assert np.linalg.norm(g) <= 1e-4 * (1.0 + f1)
+    # same basin as SciPy's trust-region solve from the same start (tolerance of the test: 1e-6 relative cost)
+    _, _, f_ref = ro.refine(prob, poses0, lms0)
+    assert f1 <= f_ref * (1 + 1e-6) + 1e-9
+
+
+@pytest.mark.gpu
+def test_refine_batch_matches_single_and_custom_start(built_lib):
+    """A batch refines every instance as if alone (bit-identical costs); a caller-supplied start is honoured."""
+    from score_b200 import generators
+    from score_b200.lowering import concat, lower_manhattan_arrays
+    from score_b200.solver import ScoreSolver
+
+    probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + 10 + i, n_robots=3 + i % 2,
+                                                                   n_steps=16 + 2 * i), "QCQP", with_names=False) for i in range(4)]
+    singles = []
+    for p in probs:
+        with ScoreSolver(p) as s:
+            s.solve()
+            rec, _ = s.refine()
+            singles.append((rec[0], s.refined()))
+    with ScoreSolver(concat(probs)) as s:
+        s.solve()
+        rec, stats = s.refine()
+        poses, lms = s.refined()
+        assert stats["n_converged"] == 4  # small graphs: every instance stops by the tolerance
+        batch = concat(probs)
+        for i, (r1, (p1, l1)) in enumerate(singles):
+            assert rec[i]["cost_final"] == r1["cost_final"] and rec[i]["outer_iterations"] == r1["outer_iterations"]
+            assert np.array_equal(poses[batch.pose_off[i]:batch.pose_off[i + 1]], p1)
+            assert np.array_equal(lms[batch.lm_off[i]:batch.lm_off[i + 1]], l1)
+        # restart from the refined point: already stationary, nothing to gain
+        rec2, _ = s.refine(init=(poses, lms))
+        assert np.all(rec2["cost_final"] <= rec["cost_final"] * (1 + 1e-12))
+        assert np.allclose(rec2["cost_initial"], rec["cost_final"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        with ScoreSolver(probs[0]) as s:
+            s.solve()
+            s.refine(init=(np.zeros((1, 2, 3)), np.zeros((1, 2))))
+
+
+@pytest.mark.gpu
+def test_refine_before_solve_is_an_error(built_lib):
+    from score_b200.solver import ScoreSolver
+
+    prob, _ = _graph(2)
+    with ScoreSolver(prob) as s:
+        with pytest.raises(RuntimeError):
+            s.refine()
+        with pytest.raises(RuntimeError):
+            s.refined()
+
+
+@pytest.mark.gpu
+def test_refinement_improves_the_trajectory_error(built_lib):
+    """The relaxation contracts the trajectory (~58 m RMSE on GOATS before any local search); from its
+    rounded estimate the refinement must land much closer to the ground truth (SE(2)-aligned ATE, whole instance)."""
+    from score_b200 import generators
+    from score_b200.evaluate import trajectory_ate
+    from score_b200.lowering import lower_manhattan_arrays
+    from score_b200.solver import ScoreSolver
+
+    arr = generators.manhattan_2d_arrays(generators.MC_BASE_SEED + 1, n_robots=4, n_steps=40)
+    prob = lower_manhattan_arrays(arr, "QCQP", with_names=False)
+    gt = arr["pos"].reshape(-1, 2)
+    with ScoreSolver(prob) as s:
+        s.solve()
+        relaxed = s.solution()[0]
+        rec, stats = s.refine()
+        poses, _ = s.refined()
+    before = float(trajectory_ate(relaxed[:, :, 2], gt)[0][0])
+    after = float(trajectory_ate(poses[:, :, 2], gt)[0][0])
+    assert rec["cost_final"][0] < rec["cost_initial"][0]
+    assert after < 0.5 * before and after < 1.0  # metres; range noise is 1 m, odometry 1 cm per step
+
+
+@pytest.mark.gpu
+def test_solve_and_refine_entry_point(built_lib):
+    """score.solve_score.solve_and_refine on FactorGraphData objects: relaxed and refined SolverResults in input order."""
+    from score.solve_score import solve_and_refine
+    from score_b200 import generators
+
+    graphs = [generators.manhattan_2d(generators.MC_BASE_SEED + 20 + i, n_robots=3, n_steps=12 + 3 * i) for i in range(2)]
+    relaxed, refined, rec = solve_and_refine(graphs, "QCQP")
+    assert len(relaxed) == len(refined) == 2 and len(rec) == 2
+    for fg, a, b, r in zip(graphs, relaxed, refined, rec):
+        assert a.solved and list(a.poses) == list(b.poses) and a.pose_chain_names == b.pose_chain_names
+        assert r["cost_final"] < r["cost_initial"] and np.isclose(b.solver_cost, r["cost_final"])
+        first = fg.pose_variables[0][0].name
+        assert np.array_equal(b.poses[first], np.eye(3))  # pin_pose: the first pose stays [I | 0]
+        for name, T in b.poses.items():
+            assert np.allclose(T[:2, :2] @ T[:2, :2].T, np.eye(2), atol=1e-10) and np.allclose(T[2], [0, 0, 1])
+        for key, dv in b.variables.distances.items():
+            assert dv.shape == (2,) and abs(np.linalg.norm(dv) - 1.0) < 1e-9
