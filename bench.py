@@ -683,42 +683,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_per_config:
         per_config = run_per_config(per_config_inputs, local_rank)
 
-    # ---- the step after the path (SURVEY.md 8(f) rank 4): local refinement of the rounded estimates, 64 instances
-    refinement = None
-    if rank == 0 and world == 1 and not args.no_refine:
-        from score_b200 import generators
-        from score_b200.lowering import slice_instances
-        from score_b200.solver import trajectory_ate
-
-        n_ref = min(64, n_local)
-        p_ref = slice_instances(prob, 0, n_ref)
-        gt = np.concatenate([generators.manhattan_2d_arrays(generators.MC_BASE_SEED + args.first_instance + lo + i,
-                                                            n_robots=args.robots, n_steps=args.poses)["pos"].reshape(-1, 2)
-                             for i in range(n_ref)])
-        with ScoreSolver(p_ref, device=local_rank) as s_ref:
-            st_ref = s_ref.solve(kkt_tol=KKT_TOL)
-            ate0 = s_ref.ate(gt)[0]
-            s_ref.refine()  # warm-up (allocation)
-            rec_ref, rs_ref = s_ref.refine()
-            poses_ref, _ = s_ref.refined()
-        ate1 = trajectory_ate(poses_ref[:, :, 2], gt, traj_off=p_ref.pose_off, device=local_rank)[0]
-        refinement = {
-            "instances": n_ref,
-            "solve_ms": st_ref.solve_ms,
-            "refine_ms": rs_ref["refine_ms"],
-            "outer_iterations": rs_ref["outer_iterations"],
-            "converged_by_tolerance": rs_ref["n_converged"],
-            "kernel_launches": rs_ref["kernel_launches"],
-            "cost_initial_median": float(np.median(rec_ref["cost_initial"])),
-            "cost_final_median": float(np.median(rec_ref["cost_final"])),
-            "ate_m_relaxed_median": float(np.median(ate0)),
-            "ate_m_refined_median": float(np.median(ate1)),
-            "ate_m_refined_max": float(np.max(ate1)),
-            "how": "score_refine (batched Levenberg-Marquardt on the original non-convex cost, block-Jacobi PCG, csrc/refine.cuh) "
-            "from the rounded estimate of the relaxation; SE(2)-aligned absolute trajectory error per instance against the "
-            "generator's ground truth; a first, untuned implementation: reported, not part of `value`",
-        }
-
     # ---- e2e: the same step through the public API with HOST buffers every step:
     # score_create (H2D of the lowered arrays from pinned memory) + score_solve + score_get_solution (D2H) + destroy
     e2e = None
@@ -803,6 +767,43 @@ def run_gpu_arm(args, rank, local_rank, world):
         }
 
     solver.close()  # idempotent
+
+    # ---- the step after the path (SURVEY.md 8(f) rank 4): local refinement of the rounded estimates, 64 instances
+    refinement = None
+    if rank == 0 and world == 1 and not args.no_refine:
+        from score_b200 import generators
+        from score_b200.lowering import slice_instances
+        from score_b200.solver import trajectory_ate
+
+        n_ref = min(64, n_local)
+        p_ref = slice_instances(prob, 0, n_ref)
+        gt = np.concatenate([generators.manhattan_2d_arrays(generators.MC_BASE_SEED + args.first_instance + lo + i,
+                                                            n_robots=args.robots, n_steps=args.poses)["pos"].reshape(-1, 2)
+                             for i in range(n_ref)])
+        with ScoreSolver(p_ref, device=local_rank) as s_ref:
+            st_ref = s_ref.solve(kkt_tol=KKT_TOL)
+            ate0 = s_ref.ate(gt)[0]
+            s_ref.refine()  # warm-up (allocation)
+            rec_ref, rs_ref = s_ref.refine()
+            poses_ref, _ = s_ref.refined()
+        ate1 = trajectory_ate(poses_ref[:, :, 2], gt, traj_off=p_ref.pose_off, device=local_rank)[0]
+        refinement = {
+            "instances": n_ref,
+            "solve_ms": st_ref.solve_ms,
+            "refine_ms": rs_ref["refine_ms"],
+            "outer_iterations": rs_ref["outer_iterations"],
+            "converged_by_tolerance": rs_ref["n_converged"],
+            "kernel_launches": rs_ref["kernel_launches"],
+            "cost_initial_median": float(np.median(rec_ref["cost_initial"])),
+            "cost_final_median": float(np.median(rec_ref["cost_final"])),
+            "ate_m_relaxed_median": float(np.median(ate0)),
+            "ate_m_refined_median": float(np.median(ate1)),
+            "ate_m_refined_max": float(np.max(ate1)),
+            "how": "score_refine (batched Levenberg-Marquardt on the original non-convex cost, block-Jacobi PCG, csrc/refine.cuh) "
+            "from the rounded estimate of the relaxation; SE(2)-aligned absolute trajectory error per instance against the "
+            "generator's ground truth; a first, untuned implementation: reported, not part of `value`",
+        }
+
     if rank == 0:
         line = {
             "metric": METRIC,
