@@ -799,9 +799,9 @@ def run_gpu_arm(args, rank, local_rank, world):
             "ate_m_relaxed_median": float(np.median(ate0)),
             "ate_m_refined_median": float(np.median(ate1)),
             "ate_m_refined_max": float(np.max(ate1)),
-            "how": "score_refine (batched Levenberg-Marquardt on the original non-convex cost, block-Jacobi PCG, csrc/refine.cuh) "
+            "how": "score_refine (batched Levenberg-Marquardt on the original non-convex cost, PCG with the odometry-chain block LDL^T preconditioner, csrc/refine.cuh) "
             "from the rounded estimate of the relaxation; SE(2)-aligned absolute trajectory error per instance against the "
-            "generator's ground truth; a first, untuned implementation: reported, not part of `value`",
+            "generator's ground truth; reported beside the path, not part of `value`",
         }
 
     if rank == 0:

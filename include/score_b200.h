@@ -245,6 +245,8 @@ typedef struct ScoreRefineParams {
   double cg_tol;      /* PCG relative residual (preconditioned norm), <=0: 1e-4 (looser solves were seen to end in
                          other, worse local minima than an exact Levenberg-Marquardt iteration) */
   void *stream;       /* cudaStream_t, NULL: the handle's own stream */
+  int32_t preconditioner; /* 0: block LDL^T along every odometry chain segment (default); 1: block-Jacobi (A/B, tests) */
+  int32_t reserved;
 } ScoreRefineParams;
 typedef struct ScoreRefineStats {
   int32_t n_instances;

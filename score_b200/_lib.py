@@ -134,6 +134,8 @@ class ScoreRefineParams(C.Structure):
         ("lambda0", C.c_double),
         ("cg_tol", C.c_double),
         ("stream", C.c_void_p),
+        ("preconditioner", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

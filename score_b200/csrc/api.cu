@@ -632,35 +632,48 @@ static int refine_run(ScoreHandle_ *h, const RefCfg &cfg, cudaStream_t st, int *
   const DevProblem &P = h->P;
   const RefVecs &R = h->R;
   const BlockTables &T = h->T;
-  const int nb = T.n_pb, ni = P.n_inst, cgrid = (ni + 3) / 4;
+  const int nb = T.n_pb, ni = P.n_inst, cgrid = (ni + 3) / 4, sgrid = (P.n_seg + 63) / 64;
+  const int chain = cfg.chain ? 1 : 0;
+  const int *segb = chain ? P.seg_begin : nullptr;
   int n = 0;
   k_ref_visit<D, RM_COST><<<nb, kThreads, 0, st>>>(P, R, T, 0);
-  k_ref_ctrl<RC_COST0><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+  k_ref_ctrl<RC_COST0><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone, segb);
   n += 2;
   int done = 0, outer = 0;
   for (; outer < cfg.max_outer && done < ni; ++outer) {
     k_ref_visit<D, RM_LIN><<<nb, kThreads, 0, st>>>(P, R, T, 0);
-    k_ref_vec<D, RV_START><<<nb, kThreads, 0, st>>>(P, R, T);
+    k_ref_vec<D, RV_START><<<nb, kThreads, 0, st>>>(P, R, T, chain);
     SCORE_CUDA_CHECK(cudaMemsetAsync(h->ref_ndone + 1, 0, sizeof(int), st));
-    k_ref_ctrl<RC_START><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
-    n += 3;
+    n += 2;
+    if (chain) {
+      k_ref_chain_factor<D><<<sgrid, 64, 0, st>>>(P, R);
+      k_ref_chain_apply<D><<<sgrid, 64, 0, st>>>(P, R, 1);
+      n += 2;
+    }
+    k_ref_ctrl<RC_START><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone, segb);
+    n += 1;
+    if (chain) {
+      k_ref_vec<D, RV_PUPDATE><<<nb, kThreads, 0, st>>>(P, R, T, chain);  // p = s (beta = 0)
+      n += 1;
+    }
     int cg_ended = 0;
     for (int it = 0; it < cfg.max_inner; ++it) {
-      if (it > 0 && (it & 15) == 0) {  // every 16 PCG iterations: have all instances' solves ended?
+      if (it > 0 && (it & 7) == 0) {  // every 8 PCG iterations: have all instances' solves ended?
         SCORE_CUDA_CHECK(cudaMemcpyAsync(&cg_ended, h->ref_ndone + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         SCORE_CUDA_CHECK(cudaStreamSynchronize(st));
         if (cg_ended + done >= ni) break;
       }
       k_ref_visit<D, RM_HV><<<nb, kThreads, 0, st>>>(P, R, T, 0);
-      k_ref_ctrl<RC_ALPHA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
-      k_ref_vec<D, RV_UPDATE><<<nb, kThreads, 0, st>>>(P, R, T);
-      k_ref_ctrl<RC_BETA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
-      k_ref_vec<D, RV_PUPDATE><<<nb, kThreads, 0, st>>>(P, R, T);
-      n += 5;
+      k_ref_ctrl<RC_ALPHA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone, segb);
+      k_ref_vec<D, RV_UPDATE><<<nb, kThreads, 0, st>>>(P, R, T, chain);
+      if (chain) k_ref_chain_apply<D><<<sgrid, 64, 0, st>>>(P, R, 0);
+      k_ref_ctrl<RC_BETA><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone, segb);
+      k_ref_vec<D, RV_PUPDATE><<<nb, kThreads, 0, st>>>(P, R, T, chain);
+      n += 5 + chain;
     }
-    k_ref_vec<D, RV_TRIAL><<<nb, kThreads, 0, st>>>(P, R, T);
+    k_ref_vec<D, RV_TRIAL><<<nb, kThreads, 0, st>>>(P, R, T, chain);
     k_ref_visit<D, RM_COST><<<nb, kThreads, 0, st>>>(P, R, T, 1);
-    k_ref_ctrl<RC_ACCEPT><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone);
+    k_ref_ctrl<RC_ACCEPT><<<cgrid, 128, 0, st>>>(T, R, cfg, ni, h->ref_ndone, segb);
     k_ref_commit<D><<<nb, kThreads, 0, st>>>(P, R, T);
     k_ref_clear<<<grid_for(ni, 128), 128, 0, st>>>(R, ni);
     n += 5;
@@ -695,6 +708,7 @@ extern "C" int score_refine(ScoreHandle h, const ScoreRefineParams *params, cons
   cfg.rel_tol = prm.rel_tol > 0 ? prm.rel_tol : 1e-10;
   cfg.lambda0 = prm.lambda0 > 0 ? prm.lambda0 : 1e-3;
   cfg.eta = prm.cg_tol > 0 ? prm.cg_tol : 1e-4;
+  cfg.chain = prm.preconditioner != 1;  // 0 (default): odometry-chain block LDL^T; 1: block-Jacobi
   SCORE_CUDA_CHECK(cudaSetDevice(h->device));
   const DevProblem &P = h->P;
   const int d = P.d, dof = d + (d == 2 ? 1 : 3);
@@ -706,7 +720,8 @@ extern "C" int score_refine(ScoreHandle h, const ScoreRefineParams *params, cons
     RA(R.x, P.nz) RA(R.xt, P.nz) RA(R.g, P.nz) RA(R.dg, P.nz) RA(R.dl, P.nz) RA(R.r, P.nz) RA(R.s, P.nz) RA(R.p, P.nz)
     RA(R.q, P.nz)
     const size_t nblk = (size_t)P.P * dof * dof + (size_t)P.L * d * d;
-    RA(R.Db, nblk) RA(R.Mi, nblk) RA(R.part_cost, h->T.n_pb) RA(R.part_dot, h->T.n_pb) RA(R.part_aux, 2 * (size_t)h->T.n_pb) RA(R.st, P.n_inst)
+    RA(R.Db, nblk) RA(R.Mi, nblk) RA(R.Ob, (size_t)P.P * dof * dof) RA(R.Sinv, (size_t)P.P * dof * dof)
+    RA(R.Lb, (size_t)P.P * dof * dof) RA(R.part_seg, P.n_seg) RA(R.part_cost, h->T.n_pb) RA(R.part_dot, h->T.n_pb) RA(R.part_aux, 2 * (size_t)h->T.n_pb) RA(R.st, P.n_inst)
     RA(h->ref_ndone, 2)
 #undef RA
     h->ref_alloc = true;

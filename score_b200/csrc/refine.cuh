@@ -44,6 +44,10 @@ struct RefVecs {
   double *Db, *Mi;             // per pose DOF x DOF (then per landmark d x d): diagonal blocks of J^T W J / inverse of the damped blocks
   double *part_cost, *part_dot;  // per pose / landmark block partial sums
   double *part_aux;              // [2 per block] g.delta and |delta|^2 of the step on trial (predicted decrease)
+  // odometry-chain preconditioner in the tangent space: block-tridiagonal (DOF x DOF blocks) along every chain segment
+  double *Ob;        // [P x DOF x DOF] coupling block J_{p-1}^T W J_p of the odometry link into pose p (rows: pose p-1)
+  double *Sinv, *Lb; // [P x DOF x DOF] inverse pivots S_p^-1 and multipliers L_p = O_p^T S_{p-1}^-1 of the block LDL^T
+  double *part_seg;  // [n_seg] r.s over a chain segment
   RefState *st;
 };
 
@@ -257,7 +261,7 @@ __device__ __forceinline__ void ref_visit(const DevProblem &P, const RefVecs &R,
 #pragma unroll
         for (int i = 0; i < DOF * DOF; ++i) Dg[i] = 0.0;
       }
-      auto edge = [&](const int e, const int other, const bool at_j) {
+      auto edge = [&](const int e, const int other, const bool at_j, const bool link_in) {
         double Xn[BLK], tm[D], Rm[D * D], k2, tau2;
         load_pose<D>(xs, 0, other, Xn);
         load_edge<D>(P, e, tm, Rm, k2, tau2);
@@ -282,6 +286,26 @@ __device__ __forceinline__ void ref_visit(const DevProblem &P, const RefVecs &R,
           if (at_j) {
             edge_JT<D, true>(L, kw, tw, L.rt, L.rR, out);
             edge_diag<D, true>(L, kw, tw, Dg);
+            if (link_in) {  // coupling block of the odometry link (rows: pose p-1, columns: this pose)
+              constexpr int NR = RD::NR;
+              double *Ob = R.Ob + (size_t)pg * DOF * DOF;
+#pragma unroll
+              for (int a = 0; a < DOF; ++a)
+#pragma unroll
+                for (int b = 0; b < DOF; ++b) {
+                  double v = 0.0;
+                  if (a < D && b < D) {
+                    v = (a == b) ? -kw : 0.0;
+                  } else if (a >= D && b < D) {
+                    v = -kw * L.A[a - D][b];
+                  } else if (a >= D && b >= D) {
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) v -= tw * L.B[a - D][i] * L.C[b - D][i];
+                  }
+                  Ob[a * DOF + b] = v;
+                }
+              (void)NR;
+            }
 #pragma unroll
             for (int r = 0; r < D; ++r) acc_s += kw * L.rt[r] * L.rt[r];
 #pragma unroll
@@ -303,15 +327,15 @@ __device__ __forceinline__ void ref_visit(const DevProblem &P, const RefVecs &R,
         }
       };
       const int e_in = P.link_edge[pg], e_out = (p + 1 < Pi) ? P.link_edge[pg + 1] : -1;
-      if (e_in >= 0) edge(e_in, p - 1, true);
-      if (e_out >= 0) edge(e_out, p + 1, false);
+      if (e_in >= 0) edge(e_in, p - 1, true, true);
+      if (e_out >= 0) edge(e_out, p + 1, false, false);
       for (int j = P.inc_ptr[pg]; j < P.inc_ptr[pg + 1]; ++j) {
         const IncRec rec = recs[j];
         const int kind = (int)(rec.x >> kIncShift), id = (int)(rec.x & kIncMask);
         if (kind == INC_EJ) {
-          edge(id, (int)rec.z, true);
+          edge(id, (int)rec.z, true, false);
         } else if (kind == INC_EI) {
-          edge(id, (int)rec.z, false);
+          edge(id, (int)rec.z, false, false);
         } else if (kind == INC_RA || kind == INC_RB) {
           double tp[D], u[D], n2 = 0.0;
           load_trans_rec<D>(xs, rec.z, tp);
@@ -515,7 +539,7 @@ enum RefVecMode : int { RV_START = 0, RV_UPDATE = 1, RV_PUPDATE = 2, RV_TRIAL = 
 //   RV_TRIAL : xt = retract(x, dl)
 //   RV_COMMIT: x = xt where the step was accepted
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, BlockTables T) {
+__global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, BlockTables T, const int chain) {
   using RD = RefDims<D>;
   constexpr int DOF = RD::DOF, BLK = RD::BLK, D1 = RD::D1;
   __shared__ double red[kThreads / 32];
@@ -573,12 +597,13 @@ __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, B
           ss[k] = s2[k];
         }
       }
+      const bool by_chain = chain && pose;  // the chain kernel computes s (and r.s) of the poses; p = s follows it
       for (int k = 0; k < n; ++k) {
         R.dl[slot + k] = 0.0;
         R.r[slot + k] = rr[k];
         R.s[slot + k] = ss[k];
-        R.p[slot + k] = ss[k];
-        acc += rr[k] * ss[k];
+        R.p[slot + k] = chain ? 0.0 : ss[k];
+        if (!by_chain) acc += rr[k] * ss[k];
       }
     } else if (MODE == RV_UPDATE) {
       double rr[DOF], ss[DOF];
@@ -599,7 +624,7 @@ __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, B
       }
       for (int k = 0; k < n; ++k) {
         R.s[slot + k] = ss[k];
-        acc += rr[k] * ss[k];
+        if (!(chain && pose)) acc += rr[k] * ss[k];
       }
     } else if (MODE == RV_PUPDATE) {
       for (int k = 0; k < n; ++k) R.p[slot + k] = R.s[slot + k] + S.beta * R.p[slot + k];
@@ -662,16 +687,148 @@ __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, B
   }
 }
 
+template <int N>
+__device__ __forceinline__ void ld_blk(const double *src, double (&o)[N * N]) {
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) o[i] = src[i];
+}
+
+// Block LDL^T of the tangent-space chain matrix of one segment: diagonal blocks Db + lambda I, couplings Ob.  One thread
+// per segment (sequential along the chain; once per outer iteration).
+template <int D>
+__global__ void k_ref_chain_factor(DevProblem P, RefVecs R) {
+  constexpr int DOF = RefDims<D>::DOF, NN = DOF * DOF;
+  const int sg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sg >= P.n_seg) return;
+  const int inst = P.seg_inst[sg];
+  if (R.st[inst].done) return;
+  const double lam = R.st[inst].lambda;
+  const int p0 = P.seg_ptr[sg], p1 = P.seg_ptr[sg + 1], pin = P.pose_off[inst];
+  double Sp[NN];  // S_{p-1}^-1
+  bool prev_free = false;
+  for (int pg = p0; pg < p1; ++pg) {
+    double S[NN], L[NN];
+    ld_blk<DOF>(R.Db + (size_t)pg * NN, S);
+#pragma unroll
+    for (int k = 0; k < DOF; ++k) {
+      const double dk = S[k * DOF + k];
+      S[k * DOF + k] = dk + lam + ((dk > 0.0) ? 0.0 : 1.0);
+    }
+    const bool pinned = pg == pin;
+    if (pg > p0 && prev_free && !pinned) {
+      double O[NN];
+      ld_blk<DOF>(R.Ob + (size_t)pg * NN, O);
+      // L = O^T Sp ;  S -= L O
+#pragma unroll
+      for (int a = 0; a < DOF; ++a)
+#pragma unroll
+        for (int b = 0; b < DOF; ++b) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < DOF; ++m) v += O[m * DOF + a] * Sp[m * DOF + b];
+          L[a * DOF + b] = v;
+        }
+#pragma unroll
+      for (int a = 0; a < DOF; ++a)
+#pragma unroll
+        for (int b = 0; b < DOF; ++b) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < DOF; ++m) v += L[a * DOF + m] * O[m * DOF + b];
+          S[a * DOF + b] -= v;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NN; ++i) L[i] = 0.0;
+    }
+    if (pinned) {
+#pragma unroll
+      for (int i = 0; i < NN; ++i) S[i] = ((i / DOF) == (i % DOF)) ? 1.0 : 0.0;
+    }
+    spd_inverse_n<DOF>(S);
+    double *So = R.Sinv + (size_t)pg * NN, *Lo = R.Lb + (size_t)pg * NN;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+      So[i] = S[i];
+      Lo[i] = L[i];
+      Sp[i] = S[i];
+    }
+    prev_free = !pinned;
+  }
+}
+
+// s = M_chain^-1 r for the poses of one segment (forward / backward substitution) and the segment's r.s.
+template <int D>
+__global__ void k_ref_chain_apply(DevProblem P, RefVecs R, const int start) {
+  constexpr int DOF = RefDims<D>::DOF, NN = DOF * DOF, BLK = RefDims<D>::BLK;
+  const int sg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sg >= P.n_seg) return;
+  const int inst = P.seg_inst[sg];
+  if (R.st[inst].done || (!start && R.st[inst].cg_done)) return;  // (start: cg_done still holds the previous solve's flag)
+  const int p0 = P.seg_ptr[sg], p1 = P.seg_ptr[sg + 1], pin = P.pose_off[inst];
+  const long base = (long)P.zoff[inst] - (long)pin * BLK;
+  double y[DOF];
+#pragma unroll
+  for (int k = 0; k < DOF; ++k) y[k] = 0.0;
+  for (int pg = p0; pg < p1; ++pg) {  // forward: y_p = r_p - L_p y_{p-1}, kept in s
+    const double *L = R.Lb + (size_t)pg * NN;
+    const double *rp = R.r + base + (long)pg * BLK;
+    double yn[DOF];
+#pragma unroll
+    for (int a = 0; a < DOF; ++a) {
+      double v = (pg == pin) ? 0.0 : rp[a];
+#pragma unroll
+      for (int m = 0; m < DOF; ++m) v -= L[a * DOF + m] * y[m];
+      yn[a] = v;
+    }
+    double *sp = R.s + base + (long)pg * BLK;
+#pragma unroll
+    for (int a = 0; a < DOF; ++a) sp[a] = y[a] = yn[a];
+  }
+  double x[DOF], dot = 0.0;
+#pragma unroll
+  for (int k = 0; k < DOF; ++k) x[k] = 0.0;
+  for (int pg = p1 - 1; pg >= p0; --pg) {  // backward: x_p = S_p^-1 (y_p - O_{p+1} x_{p+1})
+    double *sp = R.s + base + (long)pg * BLK;
+    double t[DOF];
+#pragma unroll
+    for (int a = 0; a < DOF; ++a) t[a] = sp[a];
+    if (pg + 1 < p1 && pg != pin) {
+      const double *O = R.Ob + (size_t)(pg + 1) * NN;
+#pragma unroll
+      for (int a = 0; a < DOF; ++a)
+#pragma unroll
+        for (int m = 0; m < DOF; ++m) t[a] -= O[a * DOF + m] * x[m];
+    }
+    const double *Si = R.Sinv + (size_t)pg * NN;
+    const double *rp = R.r + base + (long)pg * BLK;
+#pragma unroll
+    for (int a = 0; a < DOF; ++a) {
+      double v = 0.0;
+#pragma unroll
+      for (int m = 0; m < DOF; ++m) v += Si[a * DOF + m] * t[m];
+      x[a] = (pg == pin) ? 0.0 : v;
+    }
+#pragma unroll
+    for (int a = 0; a < DOF; ++a) {
+      sp[a] = x[a];
+      dot += x[a] * rp[a];
+    }
+  }
+  R.part_seg[sg] = dot;
+}
+
 enum RefCtrl : int { RC_COST0 = 0, RC_START = 1, RC_ALPHA = 2, RC_BETA = 3, RC_ACCEPT = 4 };
 
 struct RefCfg {
   int max_outer, max_inner;
   double rel_tol, lambda0, eta;
+  int chain, pad;  // chain: odometry-chain preconditioner (block LDL^T per segment) instead of block-Jacobi for the poses
 };
 
 // Per-instance scalars; one warp per instance, fixed-order sums of the block partials.
 template <int MODE>
-__global__ void k_ref_ctrl(BlockTables T, RefVecs R, RefCfg cfg, int n_inst, int *n_done) {
+__global__ void k_ref_ctrl(BlockTables T, RefVecs R, RefCfg cfg, int n_inst, int *n_done, const int *seg_begin) {
   const int lane = threadIdx.x & 31;
   const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (inst >= n_inst) return;
@@ -683,6 +840,11 @@ __global__ void k_ref_ctrl(BlockTables T, RefVecs R, RefCfg cfg, int n_inst, int
   double acc = 0.0, gd = 0.0, dDd = 0.0;
   for (int b = b0 + lane; b < b1; b += 32) acc += part[b];
   acc = warp_sum(acc);
+  if ((MODE == RC_START || MODE == RC_BETA) && seg_begin) {  // chain preconditioner: r.s of the poses comes per segment
+    double a2 = 0.0;
+    for (int sg = seg_begin[inst] + lane; sg < seg_begin[inst + 1]; sg += 32) a2 += R.part_seg[sg];
+    acc += warp_sum(a2);
+  }
   if (MODE == RC_ACCEPT) {
     for (int b = b0 + lane; b < b1; b += 32) {
       gd += R.part_aux[2 * b];
@@ -696,6 +858,7 @@ __global__ void k_ref_ctrl(BlockTables T, RefVecs R, RefCfg cfg, int n_inst, int
     S.cost = S.cost0 = acc;
   } else if (MODE == RC_START) {
     S.rs = S.rs0 = acc;
+    S.beta = 0.0;
     S.cg_it = 0;
     S.cg_done = !(acc > 0.0);
     S.accepted = 0;

@@ -232,7 +232,7 @@ class ScoreSolver:
         return rmse, R, t
 
     def refine(self, max_outer: int = 0, max_inner: int = 0, rel_tol: float = 0.0, lambda0: float = 0.0, cg_tol: float = 0.0,
-               init=None):
+               init=None, preconditioner: int = 0):
         """Local refinement of the last solve's rounded estimate on the original non-convex cost (score_refine: batched
         Levenberg-Marquardt, /root/reference/README.md:63-67 — the step the paper hands to GTSAM).  ``init``: optional
         (poses [P, d, d+1] as [R|t] with R in SO(d), landmarks [L, d]) to start from instead.  Returns
@@ -242,6 +242,7 @@ class ScoreSolver:
         prm = _lib.ScoreRefineParams()
         prm.max_outer, prm.max_inner = max_outer, max_inner
         prm.rel_tol, prm.lambda0, prm.cg_tol = rel_tol, lambda0, cg_tol
+        prm.preconditioner = preconditioner
         st = _lib.ScoreRefineStats()
         inst = np.zeros(p.n_instances, dtype=_REFINE_DTYPE)
         ip = il = None

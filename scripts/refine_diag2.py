@@ -10,7 +10,7 @@ for d in (2, 3):
     prob, _ = _graph(d)
     with ScoreSolver(prob) as s:
         s.solve()
-        for kw in ({}, {"cg_tol": 1e-3}, {"cg_tol": 1e-4}, {"max_inner": 50}, {"lambda0": 1.0}):
+        for kw in ({"preconditioner": 1}, {}, {"max_inner": 50}):
             for mo in (10, 30, 100):
                 rec, st = s.refine(max_outer=mo, **kw)
-                print(f"d={d} {str(kw):40s} max_outer {mo:3d}: cost -> {rec['cost_final'][0]:.6f} outer {rec['outer_iterations'][0]} accepted {rec['accepted_steps'][0]}  {st['refine_ms']:.1f} ms launches {st['kernel_launches']}", flush=True)
+                print(f"d={d} {str(kw):30s} max_outer {mo:3d}: cost -> {rec['cost_final'][0]:.6f} outer {rec['outer_iterations'][0]} accepted {rec['accepted_steps'][0]}  {st['refine_ms']:.1f} ms launches {st['kernel_launches']} conv {st['n_converged']}", flush=True)
