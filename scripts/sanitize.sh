@@ -29,6 +29,13 @@ big = lower_grid3d_arrays(generators.grid_3d_arrays(5, n_robots=12, n_steps=12, 
 with ScoreSolver(big) as s:
     st = s.solve()
     print("3D graph with a large coarse space (Schur complement + blocked sweeps) solved", st.n_solved, "newton", st.instances[0]["newton_iters"])
+    rec, rs = s.refine(max_outer=6)
+    print("3D refinement (chain preconditioner): cost", rec["cost_initial"][0], "->", rec["cost_final"][0])
+with ScoreSolver(concat(probs)) as s:
+    s.solve()
+    rec, rs = s.refine(max_outer=6)
+    rec2, _ = s.refine(max_outer=3, preconditioner=1, max_inner=20)
+    print("batch refinement: accepted steps", rec["accepted_steps"].tolist(), "block-Jacobi", rec2["accepted_steps"].tolist())
 PY
 for tool in memcheck racecheck; do
   timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1

@@ -180,3 +180,37 @@ def test_chain_and_block_jacobi_preconditioners_agree(built_lib, d):
     assert abs(rec_c["cost_final"][0] - rec_j["cost_final"][0]) <= 1e-6 * rec_j["cost_final"][0]
     assert np.abs(pc - pj).max() < 1e-2 and np.abs(lc - lj).max() < 1e-2  # flat directions of the minimum (metres)
     assert st_c["kernel_launches"] < st_j["kernel_launches"] / 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["priors", "loop_closures", "broken_chain", "no_ranges"])
+def test_refine_on_edge_case_graphs(built_lib, kind):
+    """Landmark priors, loop closures (relative-pose factors that are not odometry links), a chain broken into two
+    segments, no ranges at all, a zero-distance landmark-landmark range: the device gradient of the linearisation
+    matches finite differences of the CPU restatement, and the refinement ends at a stationary point with a lower cost."""
+    from oracle import refine_oracle as ro
+    from score_b200 import _lib
+    from score_b200.lowering import lower_factor_graph
+    from score_b200.solver import ScoreSolver
+    from test_gpu_parity import _edge_case_graph
+
+    prob = lower_factor_graph(_edge_case_graph(kind), "QCQP")
+    d = 2
+    with ScoreSolver(prob) as s:
+        assert s.solve().n_solved == 1
+        relaxed, rounded, lms0, _ = s.solution()
+        poses0 = relaxed.copy()
+        poses0[:, :, :d] = rounded
+        s.refine(max_outer=1, max_inner=1)  # one linearisation at the start point
+        g = ro.from_device_slots(prob, s.internal(_lib.SCORE_INT_REF_GRAD))
+        J = ro.tangent_jacobian(prob, poses0, lms0)
+        g_ref = J.T @ ro.residuals(prob, poses0, lms0)
+        assert np.linalg.norm(g - g_ref) <= 1e-6 * (1.0 + np.linalg.norm(g_ref))
+        dg = ro.from_device_slots(prob, s.internal(_lib.SCORE_INT_REF_DIAG))
+        assert np.allclose(dg, np.diag(J.T @ J), rtol=1e-5, atol=1e-6 * np.abs(np.diag(J.T @ J)).max())
+        rec, stats = s.refine()
+        poses, lms = s.refined()
+    f0, f1 = ro.cost(prob, poses0, lms0), ro.cost(prob, poses, lms)
+    assert np.isclose(rec["cost_initial"][0], f0, rtol=1e-9) and np.isclose(rec["cost_final"][0], f1, rtol=1e-9)
+    assert f1 <= f0 and stats["n_converged"] == 1
+    assert np.linalg.norm(ro.tangent_gradient(prob, poses, lms)) <= 1e-4 * (1.0 + f1)
