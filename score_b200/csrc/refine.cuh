@@ -287,7 +287,6 @@ __device__ __forceinline__ void ref_visit(const DevProblem &P, const RefVecs &R,
             edge_JT<D, true>(L, kw, tw, L.rt, L.rR, out);
             edge_diag<D, true>(L, kw, tw, Dg);
             if (link_in) {  // coupling block of the odometry link (rows: pose p-1, columns: this pose)
-              constexpr int NR = RD::NR;
               double *Ob = R.Ob + (size_t)pg * DOF * DOF;
 #pragma unroll
               for (int a = 0; a < DOF; ++a)
@@ -304,7 +303,6 @@ __device__ __forceinline__ void ref_visit(const DevProblem &P, const RefVecs &R,
                   }
                   Ob[a * DOF + b] = v;
                 }
-              (void)NR;
             }
 #pragma unroll
             for (int r = 0; r < D; ++r) acc_s += kw * L.rt[r] * L.rt[r];
@@ -530,14 +528,14 @@ __device__ __forceinline__ void blk_apply(const double *Mi, const double (&r)[N]
   }
 }
 
-enum RefVecMode : int { RV_START = 0, RV_UPDATE = 1, RV_PUPDATE = 2, RV_TRIAL = 3, RV_COMMIT = 4 };
+enum RefVecMode : int { RV_START = 0, RV_UPDATE = 1, RV_PUPDATE = 2, RV_TRIAL = 3 };
 
 // Element-wise passes, one thread per pose / landmark of a block:
 //   RV_START : Mi = (Db + lambda I)^-1;  dl = 0, r = -g, s = Mi r, p = s;  partial r.s
 //   RV_UPDATE: dl += alpha p, r -= alpha q, s = Mi r;  partial r.s
 //   RV_PUPDATE: p = s + beta p
-//   RV_TRIAL : xt = retract(x, dl)
-//   RV_COMMIT: x = xt where the step was accepted
+//   RV_TRIAL : xt = retract(x, dl); partial g.dl and |dl|^2 (predicted decrease)
+// (with the chain preconditioner the poses' s and r.s come from k_ref_chain_apply, and p = s from a PUPDATE with beta = 0)
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, BlockTables T, const int chain) {
   using RD = RefDims<D>;
@@ -548,7 +546,6 @@ __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, B
   const RefState S = R.st[inst];
   if (S.done) return;
   if ((MODE == RV_UPDATE || MODE == RV_PUPDATE) && S.cg_done) return;
-  if (MODE == RV_COMMIT && !S.accepted) return;
   const int z0 = bd.z0, Pi = bd.Pi;
   double acc = 0.0, acc2 = 0.0;
   const bool pose = bd.kind == CB_POSE;
@@ -668,9 +665,6 @@ __global__ void __launch_bounds__(kThreads) k_ref_vec(DevProblem P, RefVecs R, B
       } else {
         for (int k = 0; k < D; ++k) R.xt[slot + k] = R.x[slot + k] + R.dl[slot + k];
       }
-    } else {  // RV_COMMIT
-      const int len = pose ? BLK : D;
-      for (int k = 0; k < len; ++k) R.x[slot + k] = R.xt[slot + k];
     }
   }
   if (MODE == RV_START || MODE == RV_UPDATE) {
