@@ -1,4 +1,6 @@
-"""Device gradient / Hessian-vector product of the refinement against finite differences of the oracle's residuals."""
+"""Diagnostic (kept under tests/ because it executes the oracle): device gradient / Hessian-vector product of the
+refinement against finite differences of the CPU restatement, and the cost after 1 .. 200 Levenberg-Marquardt iterations.
+    python tests/tools_refine_diag.py   (GPU box)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
