@@ -531,3 +531,90 @@ def test_g2o_roundtrip(tmp_path):
         f.write("EDGE_BEARING 0 1 0.3 10\n")
     with pytest.raises(ValueError):
         parse_g2o_file(path)
+
+
+def test_dynamic_queue_jobs_without_a_device(monkeypatch):
+    """sharding.SweepQueue over solver.HandlePool / solver.StreamedJobs with ScoreSolver replaced by a recorder: a pooled
+    handle is never used by two jobs at once (a third borrower of a sub-batch waits), streamed jobs create one handle at
+    a time and cap the solves in flight, every (step, part) job runs once, byte counts add up."""
+    import threading
+    import time
+
+    from score_b200 import generators, solver as solver_mod
+    from score_b200.lowering import concat, lower_manhattan_arrays, slice_instances
+    from score_b200.sharding import SweepQueue
+
+    probs = [lower_manhattan_arrays(generators.manhattan_2d_arrays(generators.MC_BASE_SEED + i, n_robots=2, n_steps=6))
+             for i in range(6)]
+    batch = concat(probs)
+    parts = [slice_instances(batch, a, b) for a, b in ((0, 2), (2, 3), (3, 6))]
+    lock = threading.Lock()
+    st = {"busy": {}, "overlap": 0, "creating": 0, "max_creating": 0, "solving": 0, "max_solving": 0, "made": 0}
+
+    class FakeSolver:
+        def __init__(self, prob, device=0):
+            with lock:
+                st["creating"] += 1
+                st["max_creating"] = max(st["max_creating"], st["creating"])
+                st["made"] += 1
+            time.sleep(0.005)
+            self.prob, self.h2d_bytes, self.d2h_bytes = prob, 100 * prob.n_instances, 0
+            with lock:
+                st["creating"] -= 1
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            self.close()
+
+        def close(self):
+            pass
+
+        def solve(self, **kw):
+            with lock:
+                st["overlap"] += 1 if st["busy"].get(id(self)) else 0
+                st["busy"][id(self)] = True
+                st["solving"] += 1
+                st["max_solving"] = max(st["max_solving"], st["solving"])
+            time.sleep(0.02)
+            with lock:
+                st["busy"][id(self)] = False
+                st["solving"] -= 1
+            n = self.prob.n_instances
+            inst = np.zeros(n, dtype=solver_mod._INST_DTYPE)
+            z = np.zeros(len(solver_mod.KERNEL_NAMES))
+            return solver_mod.SolveStats(n, n, 5, 7, 0.0, 0.0, 1.0, 0.0, 1.0, 0, 0, 0, 0.0, inst, kernel_ms=z,
+                                         kernel_bytes=z, kernel_count=z, kernel_bytes_total=z, cycles=3 * n)
+
+        def solution(self, out=None):
+            for a, shp in zip(out, self.solution_shapes()):
+                assert a.shape == shp
+            self.d2h_bytes = 10 * self.prob.n_instances
+            return out
+
+        def solution_shapes(self):
+            p, d = self.prob, self.prob.dim
+            return (p.P, d, d + 1), (p.P, d, d), (p.L, d), (p.K, p.dist_per)
+
+    monkeypatch.setattr(solver_mod, "ScoreSolver", FakeSolver)
+    # device-resident: 2 handles per sub-batch, 5 workers -> more borrowers than handles for the hot sub-batch
+    with solver_mod.HandlePool(parts, copies=2) as pool:
+        assert st["made"] == 6
+        costs = [float(w.cycles) for w in pool.warm()]
+        assert costs == [6.0, 3.0, 9.0]
+        with SweepQueue(3, lambda step, part, w: pool.solve(part), inflight=5) as q:
+            res = q.run(4, costs)
+    assert sorted((s, p) for s, p, _ in res) == [(s, p) for s in range(4) for p in range(3)]
+    assert all(r.n_instances == parts[p].n_instances for _, p, r in res)
+    assert st["overlap"] == 0  # no handle ran two solves at once
+    # host buffers: one create at a time, at most 2 solves in flight, per-worker output slots
+    d = batch.dim
+    slot = lambda: (np.empty((batch.P, d, d + 1)), np.empty((batch.P, d, d)), np.empty((batch.L, d)),
+                    np.empty((batch.K, batch.dist_per)))
+    st.update(max_creating=0, max_solving=0, made=0)
+    jobs = solver_mod.StreamedJobs(parts, [slot() for _ in range(3)], inflight=2)
+    with SweepQueue(3, jobs, inflight=3) as q:
+        res = q.run(2, costs)
+    assert len(res) == 6 and st["made"] == 6 and st["max_creating"] == 1 and st["max_solving"] <= 2
+    assert jobs.h2d_bytes == 2 * 100 * 6 and jobs.d2h_bytes == 2 * 10 * 6
