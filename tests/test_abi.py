@@ -48,7 +48,8 @@ def test_library_is_sm100a_only(built_lib):
 def test_struct_layouts_match_header(tmp_path, built_lib):
     from score_b200 import _lib
 
-    structs = ["ScoreProblemDesc", "ScoreParams", "ScoreInstanceStats", "ScoreStats"]
+    structs = ["ScoreProblemDesc", "ScoreParams", "ScoreInstanceStats", "ScoreStats", "ScoreRefineParams", "ScoreRefineStats",
+               "ScoreRefineInstanceStats"]
     fields = {s: [f[0] for f in getattr(_lib, s)._fields_] for s in structs}
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for s in structs:
