@@ -17,8 +17,9 @@ def _graph(d, seed=3):
 
 @pytest.mark.parametrize("d", [2, 3])
 def test_refine_oracle_cost_is_the_reference_objective_on_so_d(d):
-    """CPU only: on a point with R in SO(d) the refinement cost equals the reference's relaxed objective minimised over
-    the distance variables (the range part: w max(0, n - r)^2 relaxed vs w (n - r)^2 here, equal when n >= r)."""
+    """CPU only: the refinement cost at (poses, landmarks) IS the reference's objective (oracle restatement of
+    gurobi_utils.py:358-526) evaluated with every distance variable on the unit sphere along its range (delta = v / |v|,
+    which the relaxation only bounds by |delta| <= 1); plus a finite-difference check of the tangent parametrisation."""
     from oracle import refine_oracle as ro
     from oracle import score_oracle as so
 
@@ -33,6 +34,16 @@ def test_refine_oracle_cost_is_the_reference_objective_on_so_d(d):
     f = ro.cost(prob, poses, lms)
     r = ro.residuals(prob, poses, lms)
     assert r.shape[0] == prob.E * (d + d * d) + prob.K + prob.Lp * d and np.isclose(f, r @ r)
+    # the reference's (restated) QCQP objective at x = (poses, landmarks, delta_k = unit vector from b to a): the same number
+    from score_b200 import generators
+
+    fg = (generators.manhattan_2d(generators.MC_BASE_SEED + 3, n_robots=3, n_steps=14) if d == 2
+          else generators.grid_3d_factor_graph(_graph(3)[1]))
+    op = so.assemble(fg, so.QCQP)
+    own = np.concatenate([poses[:, :, d], lms], axis=0)
+    v = own[prob.rng_a] - own[prob.rng_b]
+    x = np.concatenate([poses.ravel(), lms.ravel(), (v / np.linalg.norm(v, axis=1, keepdims=True)).ravel()])
+    assert x.shape[0] == op.n_cols and np.isclose(so.objective(op, x), f, rtol=1e-12)
     # gradient check of the tangent parametrisation: directional derivative by finite differences
     g = ro.tangent_gradient(prob, poses, lms)
     xi = rng.normal(size=g.shape) * 1e-5
