@@ -764,6 +764,7 @@ __global__ void k_ref_chain_apply(DevProblem P, RefVecs R, const int start) {
   double y[DOF];
 #pragma unroll
   for (int k = 0; k < DOF; ++k) y[k] = 0.0;
+#pragma unroll 4  // (the loads of the next poses do not depend on the recurrence: let them be issued ahead)
   for (int pg = p0; pg < p1; ++pg) {  // forward: y_p = r_p - L_p y_{p-1}, kept in s
     const double *L = R.Lb + (size_t)pg * NN;
     const double *rp = R.r + base + (long)pg * BLK;
@@ -782,6 +783,7 @@ __global__ void k_ref_chain_apply(DevProblem P, RefVecs R, const int start) {
   double x[DOF], dot = 0.0;
 #pragma unroll
   for (int k = 0; k < DOF; ++k) x[k] = 0.0;
+#pragma unroll 4
   for (int pg = p1 - 1; pg >= p0; --pg) {  // backward: x_p = S_p^-1 (y_p - O_{p+1} x_{p+1})
     double *sp = R.s + base + (long)pg * BLK;
     double t[DOF];
